@@ -1,0 +1,343 @@
+"""Generate the golden fixtures in this directory by EXECUTING the reference (raphaelsty/mkb).
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference imports ``river.stats`` for two trivial accumulators; ``river`` is not
+installed, so a throw-away shim (Mean / RollingMean) is written to a temp dir and put on
+``sys.path``.  Nothing from the reference is copied into the repo: only the *outputs* of
+running it (scores, losses, autograd gradients, sampler draws, filter lists, ranks) are
+stored as small ``.npz`` files next to this script.
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _install_shim():
+    d = tempfile.mkdtemp(prefix="river_shim_")
+    os.makedirs(os.path.join(d, "river"))
+    with open(os.path.join(d, "river", "__init__.py"), "w") as f:
+        f.write("from . import stats\n")
+    with open(os.path.join(d, "river", "stats.py"), "w") as f:
+        f.write(
+            "import collections\n"
+            "class Mean:\n"
+            "    def __init__(self): self.n = 0; self.m = 0.0\n"
+            "    def update(self, x): self.n += 1; self.m += (x - self.m) / self.n; return self\n"
+            "    def get(self): return self.m\n"
+            "class RollingMean:\n"
+            "    def __init__(self, window_size): self.d = collections.deque(maxlen=window_size)\n"
+            "    def update(self, x): self.d.append(x); return self\n"
+            "    def get(self): return sum(self.d) / len(self.d) if self.d else 0.0\n"
+        )
+    sys.path.insert(0, d)
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+
+
+_install_shim()
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+from mkb import datasets, evaluation, losses, models, sampling  # noqa: E402
+from mkb.datasets import base as ref_base  # noqa: E402
+
+MODEL_GAMMA = {"TransE": 6.0, "DistMult": 9.0, "ComplEx": 9.0, "RotatE": 9.0}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gen_step_cases():
+    """scores / loss / autograd grads for 4 models x 2 modes x {aligned, unaligned} dims."""
+    out = {}
+    rng = np.random.RandomState(7)
+    N, R, B, K = 37, 5, 6, 7
+    ent_map = {f"e{i}": i for i in range(N)}
+    rel_map = {f"r{i}": i for i in range(R)}
+    for name, gamma in MODEL_GAMMA.items():
+        for D in (8, 5):
+            torch.manual_seed(1000 + D)
+            model = getattr(models, name)(hidden_dim=D, entities=ent_map, relations=rel_map, gamma=gamma)
+            # widen the init a little so scores are not all ~gamma and softmax weights differ
+            with torch.no_grad():
+                model.entity_embedding.mul_(3.0)
+                model.relation_embedding.mul_(3.0)
+            for mode in ("tail-batch", "head-batch"):
+                sample = np.stack(
+                    [rng.randint(N, size=B), rng.randint(R, size=B), rng.randint(N, size=B)], axis=1
+                ).astype(np.int64)
+                neg = rng.randint(N, size=(B, K)).astype(np.int64)
+                neg[0, 1] = neg[0, 0]  # duplicate negative inside a row
+                neg[1, 0] = sample[1, 0]  # negative equal to the positive's head
+                neg[2, 0] = sample[2, 2]  # negative equal to the positive's tail
+                sample[3] = sample[2]  # duplicated positive
+                weight = rng.uniform(0.1, 0.5, size=B).astype(np.float32)
+                key = f"{name}_D{D}_{mode}"
+                for tag, mdl in (("f32", model), ("f64", None)):
+                    if mdl is None:
+                        import copy
+
+                        mdl = copy.deepcopy(model).double()
+                    mdl.zero_grad()
+                    s_t = torch.from_numpy(sample)
+                    n_t = torch.from_numpy(neg)
+                    w_t = torch.from_numpy(weight)
+                    if tag == "f64":
+                        w_t = w_t.double()
+                    pos = mdl(s_t)
+                    ngs = mdl(s_t, n_t, mode)
+                    loss = losses.Adversarial(alpha=0.5)(pos, ngs, w_t)
+                    loss.backward()
+                    out[f"{key}/{tag}/pos"] = _np(pos)
+                    out[f"{key}/{tag}/neg_score"] = _np(ngs)
+                    out[f"{key}/{tag}/loss"] = _np(loss)
+                    out[f"{key}/{tag}/grad_ent"] = _np(mdl.entity_embedding.grad)
+                    out[f"{key}/{tag}/grad_rel"] = _np(mdl.relation_embedding.grad)
+                out[f"{key}/ent"] = _np(model.entity_embedding)
+                out[f"{key}/rel"] = _np(model.relation_embedding)
+                out[f"{key}/sample"] = sample
+                out[f"{key}/neg"] = neg
+                out[f"{key}/weight"] = weight
+                out[f"{key}/gamma"] = np.float64(gamma)
+                # 3-D sample path (base.py:146-151)
+                s3 = np.stack([sample[:4], sample[2:6]], axis=0)
+                out[f"{key}/sample3d"] = s3
+                out[f"{key}/f32/score3d"] = _np(model(torch.from_numpy(s3)))
+    np.savez_compressed(os.path.join(HERE, "step_cases.npz"), **out)
+    print("step_cases", len(out))
+
+
+def gen_doctest_pins():
+    """The known-answer doctests of the reference, re-executed (not transcribed)."""
+    out = {}
+    # sampling/negative_sampling.py:62-126
+    torch.manual_seed(42)
+    entities = {f"e_{i}": i for i in range(4)}
+    relations = {f"r_{i}": i for i in range(4)}
+    train = [(0, 0, 1), (1, 0, 2), (2, 0, 3), (3, 0, 1)]
+    model = models.RotatE(entities=entities, relations=relations, hidden_dim=3, gamma=3)
+    dataset = datasets.Dataset(
+        train=train, entities=entities, relations=relations, batch_size=2, seed=42, shuffle=False
+    )
+    ns = sampling.NegativeSampling(
+        size=5, train_triples=dataset.train, entities=dataset.entities, relations=dataset.relations, seed=42
+    )
+    for data in dataset:
+        sample = data["sample"]
+        break
+    neg_tail = ns.generate(sample, mode="tail-batch")
+    sc_tail = model(sample, neg_tail, mode="tail-batch")
+    neg_head = ns.generate(sample, mode="head-batch")
+    sc_head = model(sample, neg_head, mode="head-batch")
+    out["ns/ent"] = _np(model.entity_embedding)
+    out["ns/rel"] = _np(model.relation_embedding)
+    out["ns/sample"] = _np(sample)
+    out["ns/neg_tail"] = _np(neg_tail)
+    out["ns/score_tail"] = _np(sc_tail)
+    out["ns/neg_head"] = _np(neg_head)
+    out["ns/score_head"] = _np(sc_head)
+    out["ns/train"] = np.array(train, dtype=np.int64)
+    # the two pools the sampler drew (same RandomState stream, negative_sampling.py:151,166)
+    rs = np.random.RandomState(42)
+    out["ns/pool0"] = rs.randint(4, size=10)
+    out["ns/pool1"] = rs.randint(4, size=10)
+    # the doctest's printed values, for a human reading the fixture
+    out["ns/doc_score_tail"] = np.array(
+        [[-2.7508, -0.8767, -3.1058, -2.7508, -2.7508], [-2.7456, -0.8674, -2.7456, -0.8674, -0.8674]]
+    )
+    out["ns/doc_score_head"] = np.array(
+        [[-0.3654, -0.3654, -0.3654, -0.3654, -0.3654], [-1.8212, -1.8212, -1.8212, -1.8212, -1.2505]]
+    )
+
+    # utils/predict.py:76-95 — TransE on Umls, three scores pinned
+    torch.manual_seed(42)
+    umls = datasets.Umls(batch_size=2)
+    tm = models.TransE(entities=umls.entities, relations=umls.relations, hidden_dim=3, gamma=6)
+    q = torch.tensor(umls.test[:3])
+    out["predict/ent"] = _np(tm.entity_embedding)
+    out["predict/rel"] = _np(tm.relation_embedding)
+    out["predict/sample"] = _np(q)
+    out["predict/score"] = _np(tm(q)).reshape(-1)
+    out["predict/doc_score"] = np.array([-2.4270, -2.1356, -2.4053])
+    np.savez_compressed(os.path.join(HERE, "doctest_pins.npz"), **out)
+    print("doctest_pins", len(out))
+
+
+def _toy_graph(rng, N, R, T):
+    seen = set()
+    while len(seen) < T:
+        seen.add((int(rng.randint(N)), int(rng.randint(R)), int(rng.randint(N))))
+    return sorted(seen)
+
+
+def gen_sampler_and_weights():
+    """Reference sampler draws, sub-sampling weights and true-set dictionaries on a toy graph."""
+    out = {}
+    rng = np.random.RandomState(11)
+    N, R = 60, 4
+    triples = _toy_graph(rng, N, R, 400)
+    entities = {f"e{i}": i for i in range(N)}
+    relations = {f"r{i}": i for i in range(R)}
+    out["triples"] = np.array(triples, dtype=np.int64)
+    out["N"], out["R"] = np.int64(N), np.int64(R)
+    # weights (datasets/base.py:102-121)
+    td = ref_base.TrainDataset(triples=triples, entities=entities, relations=relations, mode="tail-batch", seed=42)
+    out["weights"] = np.array([float(td.weights[i]) for i in range(len(triples))], dtype=np.float32)
+    # sampler
+    size = 16
+    ns = sampling.NegativeSampling(size=size, train_triples=triples, entities=entities, relations=relations, seed=42)
+    rs = np.random.RandomState(42)
+    th_keys = sorted(ns.true_head)
+    out["true_head_keys"] = np.array(th_keys, dtype=np.int64)
+    out["true_head_sizes"] = np.array([len(ns.true_head[k]) for k in th_keys], dtype=np.int64)
+    out["true_head_members"] = np.concatenate([np.sort(ns.true_head[k]) for k in th_keys]).astype(np.int64)
+    tt_keys = sorted(ns.true_tail)
+    out["true_tail_keys"] = np.array(tt_keys, dtype=np.int64)
+    out["true_tail_sizes"] = np.array([len(ns.true_tail[k]) for k in tt_keys], dtype=np.int64)
+    out["true_tail_members"] = np.concatenate([np.sort(ns.true_tail[k]) for k in tt_keys]).astype(np.int64)
+    for step in range(6):
+        mode = "head-batch" if step % 2 == 0 else "tail-batch"
+        idx = rng.randint(len(triples), size=8)
+        sample = torch.tensor([triples[i] for i in idx])
+        negs = ns.generate(sample, mode)
+        out[f"gen{step}/sample"] = _np(sample)
+        out[f"gen{step}/mode"] = np.array(mode)
+        out[f"gen{step}/pool"] = rs.randint(N, size=2 * size)
+        out[f"gen{step}/neg"] = _np(negs)
+    np.savez_compressed(os.path.join(HERE, "sampler_cases.npz"), **out)
+    print("sampler_cases", len(out))
+
+
+def gen_eval_cases():
+    """TestDataset candidate/bias lists, per-query ranks and Evaluation.eval metrics."""
+    out = {}
+    rng = np.random.RandomState(5)
+    N, R = 50, 3
+    triples = _toy_graph(rng, N, R, 300)
+    train, valid, test = triples[:240], triples[240:270], triples[270:]
+    entities = {f"e{i}": i for i in range(N)}
+    relations = {f"r{i}": i for i in range(R)}
+    out["train"] = np.array(train, dtype=np.int64)
+    out["valid"] = np.array(valid, dtype=np.int64)
+    out["test"] = np.array(test, dtype=np.int64)
+    true_triples = train + valid + test
+    for mode in ("head-batch", "tail-batch"):
+        td = ref_base.TestDataset(
+            triples=test, true_triples=true_triples, entities=entities, relations=relations, mode=mode
+        )
+        cands, biases = [], []
+        for i in range(len(test)):
+            _, c, b, _ = td[i]
+            cands.append(_np(c))
+            biases.append(_np(b))
+        out[f"{mode}/cand"] = np.stack(cands)
+        out[f"{mode}/bias"] = np.stack(biases)
+    for name, gamma in MODEL_GAMMA.items():
+        torch.manual_seed(77)
+        D = 8
+        model = getattr(models, name)(hidden_dim=D, entities=entities, relations=relations, gamma=gamma)
+        with torch.no_grad():
+            model.entity_embedding.mul_(4.0)
+            model.relation_embedding.mul_(4.0)
+        ev = evaluation.Evaluation(
+            entities=entities, relations=relations, batch_size=4, true_triples=true_triples, num_workers=0
+        )
+        out[f"{name}/ent"] = _np(model.entity_embedding)
+        out[f"{name}/rel"] = _np(model.relation_embedding)
+        out[f"{name}/gamma"] = np.float64(gamma)
+        metrics = ev.eval(model=model, dataset=test)
+        out[f"{name}/metrics"] = np.array([metrics[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")])
+        # per-query ranks, same arithmetic as evaluation.py:237-263
+        with torch.no_grad():
+            for mode in ("head-batch", "tail-batch"):
+                s = torch.tensor(test)
+                c = torch.from_numpy(out[f"{mode}/cand"])
+                b = torch.from_numpy(out[f"{mode}/bias"])
+                sc = model(s, c, mode) + b
+                order = torch.argsort(sc, dim=1, descending=True)
+                pos = s[:, 0] if mode == "head-batch" else s[:, 2]
+                ranks = [(order[i] == pos[i]).nonzero().item() + 1 for i in range(len(test))]
+                out[f"{name}/{mode}/ranks"] = np.array(ranks, dtype=np.int64)
+                out[f"{name}/{mode}/scores"] = _np(sc)
+    np.savez_compressed(os.path.join(HERE, "eval_cases.npz"), **out)
+    print("eval_cases", len(out))
+
+
+def gen_eval_doctest():
+    """evaluation/evaluation.py:39-116 — train RotatE(dim 3) for 5 epochs on a 4-triple toy graph
+    with the doctest's own loop (note: it never calls zero_grad, so .grad accumulates), then pin
+    MRR/MR/HITS.  Stores the per-step inputs so the replacement can replay the identical
+    sequence, plus the trained tables and metrics."""
+    out = {}
+    torch.manual_seed(42)
+    train = [(0, 0, 1), (0, 1, 1), (2, 0, 3), (2, 1, 3)]
+    valid = [(0, 0, 1), (2, 1, 3)]
+    test = [(0, 0, 1), (2, 1, 3)]
+    entities = {"e0": 0, "e1": 1, "e2": 2, "e3": 3}
+    relations = {"r0": 0, "r1": 1}
+    dataset = datasets.Dataset(
+        train=train, valid=valid, test=test, entities=entities, relations=relations,
+        batch_size=2, seed=42, shuffle=False,
+    )
+    negative_sampling = sampling.NegativeSampling(
+        size=2, train_triples=dataset.train, entities=dataset.entities, relations=dataset.relations, seed=42
+    )
+    model = models.RotatE(hidden_dim=3, entities=dataset.entities, relations=dataset.relations, gamma=1)
+    out["ent0"] = _np(model.entity_embedding).copy()
+    out["rel0"] = _np(model.relation_embedding).copy()
+    optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=0.5)
+    loss = losses.Adversarial(alpha=0.5)
+    steps = 0
+    for _ in range(5):
+        for data in dataset:
+            sample, weight, mode = data["sample"], data["weight"], data["mode"]
+            positive_score = model(sample)
+            negative_sample = negative_sampling.generate(sample=sample, mode=mode)
+            negative_score = model(sample, negative_sample, mode)
+            err = loss(positive_score, negative_score, weight)
+            err.backward()
+            optimizer.step()
+            out[f"step{steps}/sample"] = _np(sample)
+            out[f"step{steps}/weight"] = _np(weight)
+            out[f"step{steps}/neg"] = _np(negative_sample)
+            out[f"step{steps}/mode"] = np.array(mode)
+            out[f"step{steps}/loss"] = _np(err)
+            steps += 1
+    out["n_steps"] = np.int64(steps)
+    out["ent_final"] = _np(model.entity_embedding)
+    out["rel_final"] = _np(model.relation_embedding)
+    out["train"] = np.array(train, dtype=np.int64)
+    out["test"] = np.array(test, dtype=np.int64)
+    model = model.eval()
+    validation = evaluation.Evaluation(
+        true_triples=train + valid + test, entities=entities, relations=relations, batch_size=2
+    )
+    m = validation.eval(model=model, dataset=test)
+    out["metrics"] = np.array([m[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")])
+    out["doc_metrics"] = np.array([0.5417, 2.25, 0.25, 1.0, 1.0])
+    np.savez_compressed(os.path.join(HERE, "eval_doctest.npz"), **out)
+    print("eval_doctest", len(out), m)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc"]
+    if "step" in which:
+        gen_step_cases()
+    if "pins" in which:
+        gen_doctest_pins()
+    if "sampler" in which:
+        gen_sampler_and_weights()
+    if "eval" in which:
+        gen_eval_cases()
+    if "evaldoc" in which:
+        gen_eval_doctest()
