@@ -1,0 +1,181 @@
+/*
+ * kge_b200.h — C ABI of libkge_b200.so: the B200 (sm_100a) kernels behind the mkb hot path.
+ *
+ * raphaelsty/mkb is pure Python/PyTorch and has NO foreign-function interface of its own: the
+ * "interface" these entry points replace is the sequence of ATen calls its per-batch loop issues.
+ * Each entry point below names the reference code (file:line under /root/reference) whose work it
+ * takes over.  The Python package `mkb_b200` binds this header with ctypes (see INTEGRATION.md for
+ * the stub a reference maintainer would add to mkb itself).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless the comment says host;
+ *   - the library never allocates, frees or keeps device memory, and holds no mutable global
+ *     state => safe to call from any host thread; the caller owns every buffer incl. workspaces;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no hidden syncs;
+ *   - return value: 0 = ok, <0 = argument error (KGE_E_*), >0 = a cudaError_t from the launch;
+ *   - tables are fp32 row-major; entity rows of ComplEx/RotatE are [re(D) | im(D)] exactly as the
+ *     reference's torch.chunk(2, dim=2) expects (mkb/models/rotate.py:76-77, complex.py:70-72);
+ *   - ids are int64 (torch.LongTensor), sample is int64[B,3] = (head, relation, tail).
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+
+typedef void* kge_stream_t; /* cudaStream_t */
+
+/* mkb/models/{transe,distmult,complex,rotate}.py */
+enum kge_model { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_ROTATE = 3 };
+/* `mode` of BaseModel.batch (mkb/models/base.py:153-164); mode=None uses the tail-batch formula */
+enum kge_mode { KGE_TAIL_BATCH = 0, KGE_HEAD_BATCH = 1 };
+
+enum kge_error {
+  KGE_OK = 0,
+  KGE_E_NULL = -1,      /* a required pointer is NULL */
+  KGE_E_SIZE = -2,      /* a size is negative / zero where it must not be / too large for the kernel */
+  KGE_E_MODEL = -3,     /* unknown model enum */
+  KGE_E_MODE = -4,      /* unknown mode enum */
+  KGE_E_ALIGN = -5,     /* a pointer is not 4-byte (float) / 8-byte (int64) aligned */
+  KGE_E_UNSUPPORTED = -6 /* shape outside what the fused kernel supports: use the unfused calls */
+};
+
+/* The two embedding tables and the model constants: BaseModel.__init__ (mkb/models/base.py:66-100).
+ * entity_dim = hidden_dim * (2 for ComplEx/RotatE, else 1); relation_dim = hidden_dim * (2 for
+ * ComplEx, else 1).  embedding_range = (gamma + 2) / hidden_dim as the reference stores it (fp32). */
+typedef struct kge_tables {
+  const float* entity;   /* [n_entity, entity_dim] */
+  const float* relation; /* [n_relation, relation_dim] */
+  int64_t n_entity;
+  int64_t n_relation;
+  int32_t hidden_dim;
+  int32_t model; /* enum kge_model */
+  float gamma;
+  float embedding_range;
+} kge_tables_t;
+
+int kge_abi_version(void);
+/* Human-readable text for a return code of this library (negative) or of CUDA (positive). */
+const char* kge_strerror(int code);
+/* Device the calling thread is bound to: SM count and compute capability (host pointers). */
+int kge_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  gather -> score.   Replaces BaseModel.batch + Model.forward:
+ *     mkb/models/base.py:132-207, transe.py:65-76, distmult.py:63-75, complex.py:65-85,
+ *     rotate.py:69-99.
+ * neg == NULL : scores[B]    = model(sample)                       (tail-batch formula)
+ * neg != NULL : scores[B,K]  = model(sample, negative_sample, mode)
+ * ------------------------------------------------------------------------------------------- */
+int kge_score_fwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                  const int64_t* neg, int64_t K, float* scores, kge_stream_t stream);
+
+/* Backward of K1 (what autograd does at mkb/compose/pipeline.py:236 for one model call):
+ * ADDS d(sum grad_scores*scores)/d(table) into the dense grad_entity [n_entity, entity_dim] and
+ * grad_relation [n_relation, relation_dim] with atomics (index_select's backward is a dense
+ * index_add_).  The caller zero-fills the buffers when it wants '=' instead of '+='. */
+int kge_score_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                  const int64_t* neg, int64_t K, const float* grad_scores, float* grad_entity,
+                  float* grad_relation, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-adversarial loss on its own.  Replaces losses.Adversarial.__call__
+ * (mkb/losses/adversarial.py:21-30).  stats[4] receives
+ *   {S_p = sum_i w_i logsig(p_i), S_n = sum_i w_i sum_j a_ij logsig(-n_ij), W = sum_i w_i,
+ *    loss = -(S_p + S_n) / (2 W)}.
+ * workspace: kge_loss_workspace_bytes(B) bytes, zero-filled once by the caller before first use.
+ * ------------------------------------------------------------------------------------------- */
+size_t kge_loss_workspace_bytes(int64_t B);
+int kge_adv_loss_fwd(const float* pos_score, const float* neg_score, const float* weight, int64_t B,
+                     int64_t K, float alpha, float* stats, void* workspace, kge_stream_t stream);
+/* grad_pos[B], grad_neg[B,K] = dL/dpos, dL/dneg (softmax weights detached, adversarial.py:25).
+ * grad_loss: device scalar upstream gradient or NULL (= 1).  stats: from the forward (uses W). */
+int kge_adv_loss_bwd(const float* pos_score, const float* neg_score, const float* weight, int64_t B,
+                     int64_t K, float alpha, const float* stats, const float* grad_loss,
+                     float* grad_pos, float* grad_neg, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  fused gather -> score(1+K) -> adversarial loss, ONE kernel.  Replaces the three calls at
+ *     mkb/compose/pipeline.py:211, :230-232, :234 (model(sample); model(sample, neg, mode); loss).
+ * Outputs: pos_score[B] and neg_score[B,K] (either may be NULL = not wanted), stats[4] as above,
+ *          coef_pos[B], coef_neg[B,K] = the per-score loss gradients up to the common factor
+ *          1/(2W):  coef_pos_i = -w_i sig(-p_i),  coef_neg_ij = w_i a_ij sig(n_ij)
+ *          (saved for K3; this is what autograd would have recomputed from the saved scores).
+ * Returns KGE_E_UNSUPPORTED when K is too large for one CTA's shared memory (use K1 + loss).
+ * ------------------------------------------------------------------------------------------- */
+int kge_fused_fwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                  const int64_t* neg, int64_t K, const float* weight, float alpha, float* pos_score,
+                  float* neg_score, float* coef_pos, float* coef_neg, float* stats, void* workspace,
+                  kge_stream_t stream);
+
+/* K3  fused backward: recompute the residuals, scatter row gradients with atomics.
+ *     Replaces error.backward() (mkb/compose/pipeline.py:236) for the fused forward above.
+ * ADDS into grad_entity / grad_relation (caller-zeroed).  The common factor is taken on the device:
+ * scale = (grad_loss ? *grad_loss : 1) / (2 * stats[2]); in a multi-GPU run the caller all-reduces
+ * stats[0..2] between K2 and K3 so every rank divides by the global sum of weights. */
+int kge_fused_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                  const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
+                  const float* stats, const float* grad_loss, float* grad_entity,
+                  float* grad_relation, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  negative sampling on the device.  Replaces NegativeSampling.generate
+ *     (mkb/sampling/negative_sampling.py:158-201) and the dictionaries of positive_triples (:7-28),
+ *     which become two CSR filters keyed by  relation * n_entity + fixed_entity:
+ *        head-batch: key (r,t) -> sorted true heads;   tail-batch: key (h,r) -> sorted true tails.
+ * kge_sample_negatives: independent Philox4x32-10 stream per output slot (seed, offset given per
+ *     call; the caller advances offset by 1 per call).  Rejected candidates (members of the true
+ *     set) are redrawn.  status (device int32, OR-ed): bit0 = key not found (the reference raises
+ *     KeyError), bit1 = a true set covers every entity.
+ * kge_filter_pool: the reference's exact semantics given the batch's host-drawn pool
+ *     (RandomState.randint(n_entity, 2*size), :166): each positive takes the first K survivors of
+ *     the shared pool, repeating cyclically when fewer survive (:176-195).  bit2 of status = no
+ *     pool entry survived (the reference would spin forever).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kge_filter_csr {
+  const int64_t* keys;    /* [n_keys] sorted ascending */
+  const int64_t* offsets; /* [n_keys + 1] */
+  const int64_t* members; /* [offsets[n_keys]] sorted inside each segment */
+  int64_t n_keys;
+} kge_filter_csr_t;
+
+int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
+                         int64_t K, int64_t n_entity, uint64_t seed, uint64_t offset,
+                         int64_t* negatives, int32_t* status, kge_stream_t stream);
+int kge_filter_pool(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
+                    int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,
+                    int64_t* negatives, int32_t* status, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  filtered all-entity ranking.  Replaces TestDataset.__getitem__ (mkb/datasets/base.py:196-241)
+ *     + Evaluation.compute_score (mkb/evaluation/evaluation.py:237-263) for head-/tail-batch:
+ *     ranks[q] = 1 + #{e unfiltered: s_e > s_pos} + #{e < pos unfiltered: s_e == s_pos}.
+ * filter may be NULL (raw ranking).  scores_out (optional, [Q, n_entity]) receives the biased
+ * scores the reference would have sorted (filtered slots = s_pos - 1e5).
+ * workspace: kge_rank_workspace_bytes(tables, Q) bytes of scratch (query vectors, positive scores,
+ * filter segments); contents need not be initialised.
+ * ------------------------------------------------------------------------------------------- */
+size_t kge_rank_workspace_bytes(const kge_tables_t* tables, int64_t Q);
+int kge_rank_all(const kge_tables_t* tables, int mode, const int64_t* queries, int64_t Q,
+                 const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out, void* workspace,
+                 kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense Adam step over one table (the user-owned torch.optim.Adam of README.md:123-126 called at
+ * mkb/compose/pipeline.py:238-240), fused with zeroing the gradient for the next step.
+ * step is 1-based.  zero_grad != 0 clears grad after use (optimizer.zero_grad()).
+ * ------------------------------------------------------------------------------------------- */
+int kge_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
+                  kge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */

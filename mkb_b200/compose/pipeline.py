@@ -1,0 +1,136 @@
+"""Training loop; mirror of mkb/compose/pipeline.py (Pipeline).
+
+Same constructor, same ``learn(model, dataset, sampling, optimizer, loss, evaluation=None)``, same
+evaluation cadence / early stopping / printed output.  The difference is inside the batch loop: when
+the (model, loss) pair is one this package knows how to fuse — any mkb_b200 model with
+``losses.Adversarial`` — the three reference calls
+
+    score = model(sample); negative_score = model(sample, negative_sample, mode); loss(...)
+
+(pipeline.py:211, :230-232, :234) run as ONE forward kernel and ``error.backward()`` as ONE backward
+kernel.  Anything else takes the generic three-call route, which still runs on the CUDA kernels.
+"""
+from __future__ import annotations
+
+import collections
+
+import torch
+
+from .. import ops
+from ..losses import Adversarial
+from ..models.base import BaseModel
+from ..utils import Bar
+
+__all__ = ["Pipeline"]
+
+
+class _RollingMean:
+    """river.stats.RollingMean(window) stand-in (pipeline.py:189): mean of the last `window` values."""
+
+    def __init__(self, window_size):
+        self._d = collections.deque(maxlen=window_size)
+
+    def update(self, x):
+        self._d.append(x)
+        return self
+
+    def get(self):
+        return sum(self._d) / len(self._d) if self._d else 0.0
+
+
+class Pipeline:
+    def __init__(self, epochs, eval_every=2000, early_stopping_rounds=3, device="cpu", fused=True,
+                 loss_every=1):
+        """``fused=False`` forces the generic three-call loop.  ``loss_every`` > 1 reads the loss back
+        to the host only every that many steps (the reference's ``error.item()`` at pipeline.py:242 is
+        a device sync per step); 1 keeps the reference behaviour."""
+        self.epochs = epochs
+        self.eval_every = eval_every
+        self.early_stopping_rounds = early_stopping_rounds
+        self.device = device
+        self.fused = fused
+        self.loss_every = max(1, int(loss_every))
+        self.metric_loss = _RollingMean(1000)
+        self.round_without_improvement_valid = 0
+        self.round_without_improvement_test = 0
+        self.history_valid = collections.defaultdict(float)
+        self.history_test = collections.defaultdict(float)
+        self.valid_scores = {}
+        self.test_scores = {}
+
+    def _can_fuse(self, model, loss):
+        return self.fused and isinstance(model, BaseModel) and type(loss) is Adversarial
+
+    def learn(self, model, dataset, sampling, optimizer, loss, evaluation=None):
+        fuse = self._can_fuse(model, loss)
+        step = 0
+        for epoch in range(self.epochs):
+            bar = Bar(dataset=dataset, update_every=10)
+            for data in bar:
+                sample = data["sample"].to(self.device)
+                mode = data["mode"]
+                weight = data["weight"].to(self.device)
+                negative_sample = sampling.generate(sample=sample, mode=mode).to(self.device)
+                if fuse:
+                    error = ops.fused_adversarial_step(
+                        model.spec, model.entity_embedding, model.relation_embedding, sample, negative_sample,
+                        weight, mode, loss.alpha)
+                else:
+                    score = model(sample)
+                    negative_score = model(sample=sample, negative_sample=negative_sample, mode=mode)
+                    error = loss(score, negative_score, weight)
+                error.backward()
+                _ = optimizer.step()
+                optimizer.zero_grad()
+                step += 1
+                if step % self.loss_every == 0:
+                    self.metric_loss.update(error.item())
+                    bar.set_description(f"Epoch: {epoch}, loss: {self.metric_loss.get():4f}")
+
+            if evaluation is not None and (epoch + 1) % self.eval_every == 0:
+                print(f"\n Epoch: {epoch}.")
+                if dataset.valid:
+                    self.valid_scores = evaluation.eval(model=model, dataset=dataset.valid)
+                    self.valid_scores.update(evaluation.eval_relations(model=model, dataset=dataset.valid))
+                    self.print_metrics(description="Validation:", metrics=self.valid_scores)
+                if dataset.test:
+                    self.test_scores = evaluation.eval(model=model, dataset=dataset.test)
+                    self.test_scores.update(evaluation.eval_relations(model=model, dataset=dataset.test))
+                    self.print_metrics(description="Test:", metrics=self.test_scores)
+                    if (self.history_test["HITS@3"] > self.test_scores["HITS@3"]
+                            and self.history_test["HITS@1"] > self.test_scores["HITS@1"]):
+                        self.round_without_improvement_test += 1
+                    else:
+                        self.round_without_improvement_test = 0
+                        self.history_test = self.test_scores
+                else:
+                    if (self.history_valid["HITS@3"] > self.valid_scores["HITS@3"]
+                            and self.history_valid["HITS@1"] > self.valid_scores["HITS@1"]):
+                        self.round_without_improvement_valid += 1
+                    else:
+                        self.round_without_improvement_valid = 0
+                        self.history_valid = self.valid_scores
+                if (self.round_without_improvement_valid == self.early_stopping_rounds
+                        or self.round_without_improvement_test == self.early_stopping_rounds):
+                    print(f"\n Early stopping at epoch {epoch}.")
+                    self.print_metrics(description="Validation:", metrics=self.valid_scores)
+                    self.print_metrics(description="Test:", metrics=self.test_scores)
+                    return self
+
+        if evaluation is not None:  # the reference dereferences evaluation unguarded here (App. B.12)
+            print(f"\n Epoch: {self.epochs - 1}. \n")
+            if dataset.valid:
+                self.valid_scores = evaluation.eval(model=model, dataset=dataset.valid)
+                self.valid_scores.update(evaluation.eval_relations(model=model, dataset=dataset.valid))
+                self.print_metrics(description="Validation:", metrics=self.valid_scores)
+            if dataset.test:
+                self.test_scores = evaluation.eval(model=model, dataset=dataset.test)
+                self.test_scores.update(evaluation.eval_relations(model=model, dataset=dataset.test))
+                self.print_metrics(description="Test:", metrics=self.test_scores)
+        return self
+
+    @classmethod
+    def print_metrics(cls, description, metrics):
+        print(f"\t {description}")
+        for metric, value in metrics.items():
+            print(f"\t\t {metric}: {value}")

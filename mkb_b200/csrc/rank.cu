@@ -1,0 +1,257 @@
+// K5: filtered all-entity ranking.
+//
+// Replaces, for head-/tail-batch link prediction, TestDataset.__getitem__'s per-query Python loop
+// over all entities (mkb/datasets/base.py:196-241) and Evaluation.compute_score's
+// score -> += filter_bias -> argsort -> position-of-the-positive (mkb/evaluation/evaluation.py:237-263).
+//
+// The rank of the positive needs no sort:
+//     rank = 1 + #{e unfiltered : s_e > s_pos} + #{e < pos unfiltered : s_e == s_pos}
+// (what a stable descending argsort yields; filtered candidates carry s_pos - 1e5 in the reference
+// and can never outrank the positive).  So the kernel is a distance-"GEMM": a 64-query x 64-entity
+// tile per CTA, 4x4 scores per thread in registers, both operand tiles staged through shared
+// memory, hidden dim streamed in chunks; every score is accumulated sequentially over d with the
+// same instruction sequence, and the positive's own score comes from the same routine, so the
+// comparison s_e > s_pos is exact and self-consistent.
+//
+// Bound: RotatE is MUFU-bound (one sqrt per query x entity x dim), TransE FP32-bound, the two
+// dot-product models FP32-FMA-bound in this fp32 formulation (tensor-core split-bf16 is a later
+// row); none is HBM-bound: the entity table is re-read once per 64 queries out of L2.
+#include "kge_common.cuh"
+
+namespace kge {
+
+constexpr int kTQ = 64, kTE = 64, kDK = 32, kPad = 68;  // tile sizes; padded row stride (floats)
+
+// acc <- acc (+) term, one fixed instruction sequence shared by every caller
+template <int M>
+__device__ __forceinline__ float cand_acc(float acc, float q0, float q1, float e0, float e1) {
+  if constexpr (M == KGE_TRANSE) {
+    return __fadd_rn(acc, fabsf(__fsub_rn(e0, q0)));
+  } else if constexpr (M == KGE_DISTMULT) {
+    return __fmaf_rn(q0, e0, acc);
+  } else if constexpr (M == KGE_COMPLEX) {
+    return __fmaf_rn(q1, e1, __fmaf_rn(q0, e0, acc));
+  } else {
+    const float dx = __fsub_rn(q0, e0), dy = __fsub_rn(q1, e1);
+    return __fadd_rn(acc, sqrt_approx(__fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+  }
+}
+
+struct RankParams {
+  const float* ent;
+  const float* rel;
+  const int64_t* queries;
+  kge_filter_csr_t filter;
+  int has_filter;
+  float* qmat;        // [Q][NC*D]
+  float* pos_score;   // [Q]
+  int64_t* seg;       // [Q][2]
+  unsigned long long* ranks;
+  float* scores_out;  // optional [Q][N]
+  int64_t N;
+  int Q, D;
+  int ent_stride, rel_stride;
+  float gamma, phase_div;
+};
+
+__device__ __forceinline__ int64_t rk_find_key(const int64_t* __restrict__ keys, int64_t n, int64_t key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(keys + mid) < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return (lo < n && __ldg(keys + lo) == key) ? lo : -1;
+}
+__device__ __forceinline__ bool rk_member(const int64_t* __restrict__ m, int64_t lo, int64_t hi, int64_t x) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t v = __ldg(m + mid);
+    if (v < x) lo = mid + 1;
+    else if (v > x) hi = mid;
+    else return true;
+  }
+  return false;
+}
+
+// 1. per query: the query vector, the positive's score, the filter segment, rank := 1
+template <int M, bool HEAD>
+__global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
+  using T = Traits<M>;
+  const int qi = blockIdx.x;
+  const int64_t h = p.queries[3 * qi], r = p.queries[3 * qi + 1], t = p.queries[3 * qi + 2];
+  const float* fixed = p.ent + (HEAD ? t : h) * (int64_t)p.ent_stride;
+  const float* relrow = p.rel + r * (int64_t)p.rel_stride;
+  float* q = p.qmat + (int64_t)qi * p.ent_stride;
+  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+    const float a0 = fixed[d], a1 = T::NC == 2 ? fixed[p.D + d] : 0.f;
+    float r0, r1, q0, q1;
+    rel_effective<M>(relrow[d], T::RC == 2 ? relrow[p.D + d] : 0.f, p.phase_div, r0, r1);
+    make_query<M, HEAD>(a0, a1, r0, r1, q0, q1);
+    q[d] = q0;
+    if constexpr (T::NC == 2) q[p.D + d] = q1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float* e = p.ent + (HEAD ? h : t) * (int64_t)p.ent_stride;
+    float acc = 0.f;
+    for (int d = 0; d < p.D; ++d)
+      acc = cand_acc<M>(acc, q[d], T::NC == 2 ? q[p.D + d] : 0.f, e[d], T::NC == 2 ? e[p.D + d] : 0.f);
+    p.pos_score[qi] = finish_score<M>(acc, p.gamma);
+    p.ranks[qi] = 1ull;
+    int64_t lo = 0, hi = 0;
+    if (p.has_filter) {
+      const int64_t k = rk_find_key(p.filter.keys, p.filter.n_keys, r * p.N + (HEAD ? t : h));
+      if (k >= 0) {
+        lo = p.filter.offsets[k];
+        hi = p.filter.offsets[k + 1];
+      }
+    }
+    p.seg[2 * qi] = lo;
+    p.seg[2 * qi + 1] = hi;
+  }
+}
+
+// 2. 64 x 64 tile of scores, compare + count
+template <int M, bool HEAD>
+__global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
+  using T = Traits<M>;
+  __shared__ __align__(16) float qs[T::NC][kDK][kPad];
+  __shared__ __align__(16) float es[T::NC][kDK][kPad];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int q_base = blockIdx.x * kTQ;
+  const int64_t e_base = (int64_t)blockIdx.y * kTE;
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  for (int d0 = 0; d0 < p.D; d0 += kDK) {
+    __syncthreads();
+    const int d = d0 + lane;
+    for (int row = warp; row < kTQ; row += kWarps) {
+      const int qi = q_base + row;
+      const int64_t ei = e_base + row;
+      const bool vq = qi < p.Q && d < p.D, ve = ei < p.N && d < p.D;
+      const float* qrow = p.qmat + (int64_t)qi * p.ent_stride;
+      const float* erow = p.ent + ei * (int64_t)p.ent_stride;
+#pragma unroll
+      for (int c = 0; c < T::NC; ++c) {
+        qs[c][lane][row] = vq ? qrow[c * p.D + d] : 0.f;
+        es[c][lane][row] = ve ? __ldg(erow + c * p.D + d) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int dd = 0; dd < kDK; ++dd) {
+      const float4 qa = *reinterpret_cast<const float4*>(&qs[0][dd][ty * 4]);
+      const float4 ea = *reinterpret_cast<const float4*>(&es[0][dd][tx * 4]);
+      float4 qb = make_float4(0.f, 0.f, 0.f, 0.f), eb = qb;
+      if constexpr (T::NC == 2) {
+        qb = *reinterpret_cast<const float4*>(&qs[1][dd][ty * 4]);
+        eb = *reinterpret_cast<const float4*>(&es[1][dd][tx * 4]);
+      }
+      const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
+      const float e0[4] = {ea.x, ea.y, ea.z, ea.w}, e1[4] = {eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = cand_acc<M>(acc[a][b], q0[a], q1[a], e0[b], e1[b]);
+    }
+  }
+
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int qi = q_base + ty * 4 + a;
+    const bool vq = qi < p.Q;  // uniform over the 16 threads that share ty
+    unsigned cnt = 0;
+    if (vq) {
+      const float sp = p.pos_score[qi];
+      const int64_t pos = p.queries[3 * qi + (HEAD ? 0 : 2)];
+      const int64_t lo = p.seg[2 * qi], hi = p.seg[2 * qi + 1];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t e = e_base + tx * 4 + b;
+        if (e < p.N) {
+          const float s = finish_score<M>(acc[a][b], p.gamma);
+          const bool beats = (s > sp) || (s == sp && e < pos);
+          bool filtered = false;
+          if ((beats || p.scores_out) && e != pos && hi > lo)
+            filtered = rk_member(p.filter.members, lo, hi, e);
+          if (beats && e != pos && !filtered) ++cnt;
+          if (p.scores_out) p.scores_out[(int64_t)qi * p.N + e] = filtered ? sp + (-1e5f) : s;
+        }
+      }
+    }
+    // the 16 threads with the same ty sit in one half-warp: fold before the atomic
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+    if (vq && tx == 0 && cnt) atomicAdd(p.ranks + qi, (unsigned long long)cnt);
+  }
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" size_t kge_rank_workspace_bytes(const kge_tables_t* t, int64_t Q) {
+  if (!t || Q <= 0) return 0;
+  const size_t row = (size_t)t->hidden_dim * entity_comps(t->model);
+  return (size_t)Q * (row * sizeof(float) + sizeof(float) + 2 * sizeof(int64_t)) + 64;
+}
+
+extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* queries, int64_t Q,
+                            const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out,
+                            void* workspace, kge_stream_t stream) {
+  if (!t || !t->entity || !t->relation || !queries || !ranks || !workspace) return KGE_E_NULL;
+  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  if (Q < 0 || Q > INT32_MAX / kTQ || t->hidden_dim <= 0 || t->n_entity <= 0) return KGE_E_SIZE;
+  if (Q == 0) return KGE_OK;
+  RankParams p{};
+  p.ent = t->entity;
+  p.rel = t->relation;
+  p.queries = queries;
+  p.has_filter = filter && filter->n_keys > 0;
+  if (p.has_filter) p.filter = *filter;
+  p.N = t->n_entity;
+  p.Q = (int)Q;
+  p.D = t->hidden_dim;
+  p.ent_stride = t->hidden_dim * entity_comps(t->model);
+  p.rel_stride = t->hidden_dim * relation_comps(t->model);
+  p.gamma = t->gamma;
+  p.phase_div = host_phase_div(t->embedding_range);
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.seg = reinterpret_cast<int64_t*>(ws);
+  ws += (size_t)Q * 2 * sizeof(int64_t);
+  p.qmat = reinterpret_cast<float*>(ws);
+  ws += (size_t)Q * p.ent_stride * sizeof(float);
+  p.pos_score = reinterpret_cast<float*>(ws);
+  p.ranks = reinterpret_cast<unsigned long long*>(ranks);
+  p.scores_out = scores_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((Q + kTQ - 1) / kTQ), (unsigned)((p.N + kTE - 1) / kTE));
+  if (grid.y > 65535) return KGE_E_SIZE;
+#define KGE_CASE(MM)                                                            \
+  case MM:                                                                      \
+    if (mode == KGE_HEAD_BATCH) {                                               \
+      rank_prepare_kernel<MM, true><<<(unsigned)Q, kThreads, 0, st>>>(p);       \
+      rank_tile_kernel<MM, true><<<grid, kThreads, 0, st>>>(p);                 \
+    } else {                                                                    \
+      rank_prepare_kernel<MM, false><<<(unsigned)Q, kThreads, 0, st>>>(p);      \
+      rank_tile_kernel<MM, false><<<grid, kThreads, 0, st>>>(p);                \
+    }                                                                           \
+    break;
+  switch (t->model) {
+    KGE_CASE(KGE_TRANSE)
+    KGE_CASE(KGE_DISTMULT)
+    KGE_CASE(KGE_COMPLEX)
+    KGE_CASE(KGE_ROTATE)
+  }
+#undef KGE_CASE
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}

@@ -1,0 +1,654 @@
+// K1/K2/K3: gather -> score (-> self-adversarial loss) forward and the atomic-scatter backward.
+//
+// Work decomposition
+//   forward : one CTA per positive triple.  The CTA builds the positive's *query* vector
+//             (h∘r, h+r, conj(r)∘t, ... — everything that does not depend on the candidate) once in
+//             shared memory, then its 8 warps stream the K candidate rows: one warp per candidate,
+//             16-byte coalesced loads of the row, fp32 accumulate, warp-shuffle reduction over the
+//             hidden dim.  In the fused variant the K scores never leave shared memory before the
+//             softmax-weighted loss terms and the backward coefficients are formed; a ticket
+//             counter lets the last CTA fold the per-positive partial sums in a fixed order.
+//   backward: one CTA per positive (x K-slices).  Threads own hidden-dim elements, so the
+//             candidate-row gradient needs no reduction at all: each thread recomputes its residual,
+//             fires a vector RED into the dense gradient row of the candidate, and keeps the
+//             query-side gradient in registers; after the K loop one RED per element goes to the
+//             head / relation / tail rows of the positive.
+//
+// Reference being replaced: mkb/models/base.py:132-207 (gathers), transe.py:65-76,
+// distmult.py:63-75, complex.py:65-85, rotate.py:69-99 (scores), losses/adversarial.py:21-30,
+// and autograd's backward of all of them (compose/pipeline.py:236).
+#include "kge_common.cuh"
+
+namespace kge {
+
+struct FwdParams {
+  const float* ent;
+  const float* rel;
+  const int64_t* sample;
+  const int64_t* neg;
+  const float* weight;
+  float* pos_score;
+  float* neg_score;
+  float* coef_pos;
+  float* coef_neg;
+  float* partials;       // [3, B]
+  unsigned int* ticket;  // zero on entry, reset by the last CTA
+  float* stats;          // [4]
+  int B, K, D, Dp;
+  int ent_stride, rel_stride;
+  int k_per_cta;
+  float gamma, phase_div, alpha;
+};
+
+// ------------------------------------------------------------------------------------------------
+// positives only: one warp per triple (model(sample) and the 3-D sample path)
+// ------------------------------------------------------------------------------------------------
+template <int M, int VEC>
+__global__ void __launch_bounds__(kThreads) score_pos_kernel(FwdParams p) {
+  using T = Traits<M>;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (i >= p.B) return;
+  const float* h = p.ent + p.sample[3 * i + 0] * (int64_t)p.ent_stride;
+  const float* r = p.rel + p.sample[3 * i + 1] * (int64_t)p.rel_stride;
+  const float* t = p.ent + p.sample[3 * i + 2] * (int64_t)p.ent_stride;
+  float acc = 0.f;
+  for (int d = lane * VEC; d < p.D; d += 32 * VEC) {
+    float h0[VEC], h1[VEC] = {}, rr0[VEC], rr1[VEC] = {}, t0[VEC], t1[VEC] = {};
+    ld_global<VEC>(h + d, h0);
+    ld_global<VEC>(r + d, rr0);
+    ld_global<VEC>(t + d, t0);
+    if constexpr (T::NC == 2) {
+      ld_global<VEC>(h + p.D + d, h1);
+      ld_global<VEC>(t + p.D + d, t1);
+    }
+    if constexpr (T::RC == 2) ld_global<VEC>(r + p.D + d, rr1);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float r0, r1, q0, q1;
+      rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0, r1);
+      make_query<M, false>(h0[v], h1[v], r0, r1, q0, q1);
+      acc += cand_term<M>(q0, q1, t0[v], t1[v]);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) p.pos_score[i] = finish_score<M>(acc, p.gamma);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one candidate row against the query in shared memory (one warp)
+// ------------------------------------------------------------------------------------------------
+template <int M, int VEC>
+__device__ __forceinline__ float row_reduce(const float* __restrict__ row, const float* __restrict__ q,
+                                            int D, int Dp, int lane) {
+  using T = Traits<M>;
+  constexpr int U = 4;  // row chunks in flight per lane
+  float acc = 0.f;
+  for (int d0 = lane * VEC; d0 < D; d0 += 32 * VEC * U) {
+    float e0[U][VEC], e1[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int d = d0 + u * 32 * VEC;
+      if (d < D) {
+        ld_global<VEC>(row + d, e0[u]);
+        if constexpr (T::NC == 2) ld_global<VEC>(row + D + d, e1[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int d = d0 + u * 32 * VEC;
+      if (d < D) {
+        float q0[VEC], q1[VEC] = {};
+        ld_shared<VEC>(q + d, q0);
+        if constexpr (T::NC == 2) ld_shared<VEC>(q + Dp + d, q1);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          acc += cand_term<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f);
+      }
+    }
+  }
+  return warp_sum(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward with candidates: grid = (B, K-slices); FUSED => K-slices == 1 and the loss is folded in
+// ------------------------------------------------------------------------------------------------
+template <int M, bool HEAD, int VEC, bool FUSED>
+__global__ void __launch_bounds__(kThreads) score_neg_kernel(FwdParams p) {
+  using T = Traits<M>;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[33];
+  float* q = smem;                  // [NC][Dp]
+  float* sc = smem + T::NC * p.Dp;  // FUSED: [K]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i = blockIdx.x;
+  const int64_t hid = p.sample[3 * i + 0], rid = p.sample[3 * i + 1], tidx = p.sample[3 * i + 2];
+  const float* fixed = p.ent + (HEAD ? tidx : hid) * (int64_t)p.ent_stride;
+  const float* relrow = p.rel + rid * (int64_t)p.rel_stride;
+  const bool want_pos = (FUSED || p.pos_score != nullptr) && blockIdx.y == 0;
+
+  // 1. query -> shared memory (and, in head-batch, the tail-form positive on the fly)
+  float pacc = 0.f;
+  for (int d = tid * VEC; d < p.D; d += kThreads * VEC) {
+    float a0[VEC], a1[VEC] = {}, rr0[VEC], rr1[VEC] = {}, q0[VEC], q1[VEC];
+    ld_global<VEC>(fixed + d, a0);
+    if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
+    ld_global<VEC>(relrow + d, rr0);
+    if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
+    float r0[VEC], r1[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
+      make_query<M, HEAD>(a0[v], a1[v], r0[v], r1[v], q0[v], q1[v]);
+    }
+    st_shared<VEC>(q + d, q0);
+    if constexpr (T::NC == 2) st_shared<VEC>(q + p.Dp + d, q1);
+    if (want_pos) {
+      // positive = tail-batch formula on (h, r, t)   (compose/pipeline.py:211, mode=None)
+      const float* hrow = p.ent + hid * (int64_t)p.ent_stride;
+      const float* trow = p.ent + tidx * (int64_t)p.ent_stride;
+      float t0[VEC], t1[VEC] = {};
+      ld_global<VEC>(trow + d, t0);
+      if constexpr (T::NC == 2) ld_global<VEC>(trow + p.D + d, t1);
+      if constexpr (HEAD) {
+        float h0[VEC], h1[VEC] = {};
+        ld_global<VEC>(hrow + d, h0);
+        if constexpr (T::NC == 2) ld_global<VEC>(hrow + p.D + d, h1);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float qp0, qp1;
+          make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1);
+          pacc += cand_term<M>(qp0, qp1, t0[v], t1[v]);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) pacc += cand_term<M>(q0[v], q1[v], t0[v], t1[v]);
+      }
+    }
+  }
+  float pos = 0.f;
+  if (want_pos) {  // uniform across the CTA
+    pos = finish_score<M>(block_sum(pacc, red), p.gamma);
+    if (tid == 0 && p.pos_score) p.pos_score[i] = pos;
+  }
+  __syncthreads();
+
+  // 2. candidates: warp w takes j = j0 + w, j0 + w + 8, ...; indices are prefetched 32 at a time
+  const int j0 = blockIdx.y * p.k_per_cta;
+  const int j1 = min(p.K, j0 + p.k_per_cta);
+  const int64_t* negrow = p.neg + i * (int64_t)p.K;
+  for (int jb = j0 + warp; jb < j1; jb += kWarps * 32) {
+    const int jmine = jb + lane * kWarps;
+    const int64_t my_id = jmine < j1 ? negrow[jmine] : 0;
+    const int cnt = min(32, (j1 - jb + kWarps - 1) / kWarps);
+    for (int m = 0; m < cnt; ++m) {
+      const int64_t id = __shfl_sync(kFull, my_id, m);
+      const float acc = row_reduce<M, VEC>(p.ent + id * (int64_t)p.ent_stride, q, p.D, p.Dp, lane);
+      if (lane == 0) {
+        const int j = jb + m * kWarps;
+        const float s = finish_score<M>(acc, p.gamma);
+        if (p.neg_score) p.neg_score[i * (int64_t)p.K + j] = s;
+        if constexpr (FUSED) sc[j] = s;
+      }
+    }
+  }
+
+  if constexpr (FUSED) {
+    // 3. self-adversarial terms for this positive  (losses/adversarial.py:22-30)
+    __syncthreads();
+    const float w = p.weight[i];
+    const float nt = adv_row_terms(sc, p.K, p.alpha, w, p.coef_neg + i * (int64_t)p.K, red);
+    if (tid == 0) {
+      p.coef_pos[i] = -w * sigmoid(-pos);
+      p.partials[i] = w * log_sigmoid(pos);
+      p.partials[p.B + i] = w * nt;
+      p.partials[2 * p.B + i] = w;
+    }
+    // 4. last CTA folds the partials in a fixed order (deterministic loss)
+    fold_partials(p.partials, p.B, p.ticket, gridDim.x, p.stats, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdParams {
+  const float* ent;
+  const float* rel;
+  const int64_t* sample;
+  const int64_t* neg;
+  const float* gpos;   // [B] or null
+  const float* gneg;   // [B,K] or null
+  const float* stats;  // null => scale 1
+  const float* grad_loss;
+  float* grad_ent;
+  float* grad_rel;
+  int B, K, D;
+  int ent_stride, rel_stride;
+  int k_per_cta;
+  int tpg;  // threads per group (multiple of 32, divides 256)
+  float phase_div;
+};
+
+constexpr int kTileK = 256;
+
+template <int M, bool HEAD, int VEC>
+__global__ void __launch_bounds__(kThreads) score_bwd_kernel(BwdParams p) {
+  using T = Traits<M>;
+  extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC]
+  __shared__ int64_t s_idx[kTileK];
+  __shared__ float s_coef[kTileK];
+
+  const int tid = threadIdx.x;
+  const int tpg = p.tpg, G = kThreads / tpg;
+  const int grp = tid / tpg, lt = tid - grp * tpg;
+  const int64_t i = blockIdx.x;
+  const int64_t hid = p.sample[3 * i + 0], rid = p.sample[3 * i + 1], tidx = p.sample[3 * i + 2];
+  const float* hrow = p.ent + hid * (int64_t)p.ent_stride;
+  const float* trow = p.ent + tidx * (int64_t)p.ent_stride;
+  const float* fixed = HEAD ? trow : hrow;
+  const float* relrow = p.rel + rid * (int64_t)p.rel_stride;
+  float scale = 1.f;
+  if (p.stats) scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * __ldg(p.stats + 2));
+  const bool do_pos = (p.gpos != nullptr) && blockIdx.y == 0;
+  const float cpos = do_pos ? scale * __ldg(p.gpos + i) : 0.f;
+  const int j0 = p.neg ? blockIdx.y * p.k_per_cta : 0;
+  const int j1 = p.neg ? min(p.K, j0 + p.k_per_cta) : 0;
+
+  for (int cb = 0; cb * tpg * VEC < p.D; ++cb) {
+    const int d = (cb * tpg + lt) * VEC;
+    const bool active = d < p.D;
+    float a0[VEC] = {}, a1[VEC] = {}, r0[VEC] = {}, r1[VEC] = {}, q0[VEC] = {}, q1[VEC] = {};
+    float dq0[VEC] = {}, dq1[VEC] = {};
+    if (active) {
+      float rr0[VEC], rr1[VEC] = {};
+      ld_global<VEC>(fixed + d, a0);
+      if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
+      ld_global<VEC>(relrow + d, rr0);
+      if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
+        make_query<M, HEAD>(a0[v], a1[v], r0[v], r1[v], q0[v], q1[v]);
+      }
+    }
+    // ---- candidates: group g takes every G-th row of the tile
+    for (int jt = j0; jt < j1; jt += kTileK) {
+      const int n = min(kTileK, j1 - jt);
+      __syncthreads();
+      for (int k = tid; k < n; k += kThreads) {
+        s_idx[k] = p.neg[i * (int64_t)p.K + jt + k];
+        s_coef[k] = scale * p.gneg[i * (int64_t)p.K + jt + k];
+      }
+      __syncthreads();
+      if (active) {
+        constexpr int U = 4;
+        for (int jj = grp; jj < n; jj += G * U) {
+          float e0[U][VEC], e1[U][VEC];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int k = jj + u * G;
+            if (k < n) {
+              const float* row = p.ent + s_idx[k] * (int64_t)p.ent_stride;
+              ld_global<VEC>(row + d, e0[u]);
+              if constexpr (T::NC == 2) ld_global<VEC>(row + p.D + d, e1[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int k = jj + u * G;
+            if (k < n) {
+              const float c = s_coef[k];
+              float* grow = p.grad_ent + s_idx[k] * (int64_t)p.ent_stride;
+              float g0[VEC], g1[VEC];
+#pragma unroll
+              for (int v = 0; v < VEC; ++v)
+                cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
+                            dq0[v], dq1[v]);
+              red_add<VEC>(grow + d, g0);
+              if constexpr (T::NC == 2) red_add<VEC>(grow + p.D + d, g1);
+            }
+          }
+        }
+      }
+    }
+    // ---- fold the groups' query gradients into group 0
+    if (G > 1) {
+      __syncthreads();
+      if (grp > 0 && active) {
+        float* dst = smem + (size_t)(grp - 1) * T::NC * tpg * VEC + lt * VEC;
+        st_shared<VEC>(dst, dq0);
+        if constexpr (T::NC == 2) st_shared<VEC>(dst + tpg * VEC, dq1);
+      }
+      __syncthreads();
+      if (grp == 0 && active) {
+        for (int g = 1; g < G; ++g) {
+          const float* src = smem + (size_t)(g - 1) * T::NC * tpg * VEC + lt * VEC;
+          float x0[VEC], x1[VEC];
+          ld_shared<VEC>(src, x0);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) dq0[v] += x0[v];
+          if constexpr (T::NC == 2) {
+            ld_shared<VEC>(src + tpg * VEC, x1);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dq1[v] += x1[v];
+          }
+        }
+      }
+    }
+    // ---- positive term + chain rule to the positive's own rows (group 0 only)
+    if (grp == 0 && active) {
+      float gt0[VEC] = {}, gt1[VEC] = {};  // -> tail row
+      float gh0[VEC] = {}, gh1[VEC] = {};  // -> head row
+      float gr0[VEC] = {}, gr1[VEC] = {};  // -> relation row (stored form)
+      float dqp0[VEC] = {}, dqp1[VEC] = {};
+      float h0[VEC] = {}, h1[VEC] = {};
+      if (do_pos) {
+        float t0[VEC], t1[VEC] = {};
+        ld_global<VEC>(trow + d, t0);
+        if constexpr (T::NC == 2) ld_global<VEC>(trow + p.D + d, t1);
+        if constexpr (HEAD) {
+          ld_global<VEC>(hrow + d, h0);
+          if constexpr (T::NC == 2) ld_global<VEC>(hrow + p.D + d, h1);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            float qp0, qp1;
+            make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1);
+            cand_bwd<M>(qp0, qp1, t0[v], t1[v], cpos, gt0[v], gt1[v], dqp0[v], dqp1[v]);
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            cand_bwd<M>(q0[v], q1[v], t0[v], t1[v], cpos, gt0[v], gt1[v], dq0[v], dq1[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float da0, da1, dr0, dr1;
+        query_bwd<M, HEAD>(dq0[v], dq1[v], a0[v], a1[v], r0[v], r1[v], da0, da1, dr0, dr1);
+        if constexpr (HEAD) {
+          gt0[v] += da0;
+          gt1[v] += da1;
+          if (do_pos) {
+            float dh0, dh1, dpr0, dpr1;
+            query_bwd<M, false>(dqp0[v], dqp1[v], h0[v], h1[v], r0[v], r1[v], dh0, dh1, dpr0, dpr1);
+            gh0[v] = dh0;
+            gh1[v] = dh1;
+            dr0 += dpr0;
+            dr1 += dpr1;
+          }
+        } else {
+          gh0[v] = da0;
+          gh1[v] = da1;
+        }
+        rel_bwd<M>(dr0, dr1, r0[v], r1[v], p.phase_div, gr0[v], gr1[v]);
+      }
+      float* gh = p.grad_ent + hid * (int64_t)p.ent_stride;
+      float* gt = p.grad_ent + tidx * (int64_t)p.ent_stride;
+      float* gr = p.grad_rel + rid * (int64_t)p.rel_stride;
+      if (!HEAD || do_pos) {
+        red_add<VEC>(gh + d, gh0);
+        if constexpr (T::NC == 2) red_add<VEC>(gh + p.D + d, gh1);
+      }
+      if (HEAD || do_pos) {
+        red_add<VEC>(gt + d, gt0);
+        if constexpr (T::NC == 2) red_add<VEC>(gt + p.D + d, gt1);
+      }
+      red_add<VEC>(gr + d, gr0);
+      if constexpr (T::RC == 2) red_add<VEC>(gr + p.D + d, gr1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int validate_tables(const kge_tables_t* t) {
+  if (!t || !t->entity || !t->relation) return KGE_E_NULL;
+  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (t->hidden_dim <= 0 || t->n_entity <= 0 || t->n_relation <= 0) return KGE_E_SIZE;
+  if ((reinterpret_cast<uintptr_t>(t->entity) | reinterpret_cast<uintptr_t>(t->relation)) & 3u)
+    return KGE_E_ALIGN;
+  return KGE_OK;
+}
+
+static bool can_vectorize(const kge_tables_t* t, const void* a = nullptr, const void* b = nullptr) {
+  // rows (and the im half of complex rows) must start on 16-byte boundaries
+  return (t->hidden_dim % 4 == 0) && aligned16(t->entity) && aligned16(t->relation) &&
+         (!a || aligned16(a)) && (!b || aligned16(b));
+}
+
+static int sm_count() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 200 * 1024) return KGE_E_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return KGE_OK;
+}
+
+template <int M, bool HEAD, int VEC, bool FUSED>
+static int launch_neg(const FwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = score_neg_kernel<M, HEAD, VEC, FUSED>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, st>>>(p);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}
+
+template <bool FUSED>
+static int dispatch_neg(int model, int mode, bool vec, const FwdParams& p, dim3 grid, size_t smem,
+                        cudaStream_t st) {
+#define KGE_CASE(MM)                                                                        \
+  case MM:                                                                                  \
+    if (mode == KGE_HEAD_BATCH)                                                             \
+      return vec ? launch_neg<MM, true, 4, FUSED>(p, grid, smem, st)                        \
+                 : launch_neg<MM, true, 1, FUSED>(p, grid, smem, st);                       \
+    return vec ? launch_neg<MM, false, 4, FUSED>(p, grid, smem, st)                         \
+               : launch_neg<MM, false, 1, FUSED>(p, grid, smem, st);
+  switch (model) {
+    KGE_CASE(KGE_TRANSE)
+    KGE_CASE(KGE_DISTMULT)
+    KGE_CASE(KGE_COMPLEX)
+    KGE_CASE(KGE_ROTATE)
+  }
+#undef KGE_CASE
+  return KGE_E_MODEL;
+}
+
+static void fill_fwd(FwdParams& p, const kge_tables_t* t) {
+  p.ent = t->entity;
+  p.rel = t->relation;
+  p.D = t->hidden_dim;
+  p.Dp = (t->hidden_dim + 3) & ~3;
+  p.ent_stride = t->hidden_dim * entity_comps(t->model);
+  p.rel_stride = t->hidden_dim * relation_comps(t->model);
+  p.gamma = t->gamma;
+  p.phase_div = host_phase_div(t->embedding_range);
+}
+
+template <int M, bool HEAD, int VEC>
+static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = score_bwd_kernel<M, HEAD, VEC>;
+  int rc = set_smem(kern, smem);
+  if (rc) return rc;
+  kern<<<grid, kThreads, smem, st>>>(p);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}
+
+static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B, const int64_t* neg,
+                   int64_t K, const float* gpos, const float* gneg, const float* stats,
+                   const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st) {
+  BwdParams p{};
+  p.ent = t->entity;
+  p.rel = t->relation;
+  p.sample = sample;
+  p.neg = neg;
+  p.gpos = gpos;
+  p.gneg = gneg;
+  p.stats = stats;
+  p.grad_loss = grad_loss;
+  p.grad_ent = grad_ent;
+  p.grad_rel = grad_rel;
+  p.B = (int)B;
+  p.K = neg ? (int)K : 0;
+  p.D = t->hidden_dim;
+  p.ent_stride = t->hidden_dim * entity_comps(t->model);
+  p.rel_stride = t->hidden_dim * relation_comps(t->model);
+  p.phase_div = host_phase_div(t->embedding_range);
+  const bool vec = can_vectorize(t, grad_ent, grad_rel);
+  const int VEC = vec ? 4 : 1;
+  const int chunks = (p.D + VEC - 1) / VEC;
+  int tpg = 32;
+  while (tpg < kThreads && tpg < chunks) tpg <<= 1;
+  p.tpg = tpg;
+  const int G = kThreads / tpg;
+  // K-slices: enough CTAs to fill the machine when B alone is small
+  int ks = 1;
+  if (p.K > 0) {
+    const int want = (4 * sm_count() + (int)B - 1) / (int)B;
+    const int maxks = (p.K + 63) / 64;
+    ks = want < 1 ? 1 : (want > maxks ? maxks : want);
+  }
+  p.k_per_cta = p.K > 0 ? (p.K + ks - 1) / ks : 0;
+  if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
+  dim3 grid((unsigned)B, (unsigned)ks);
+  const size_t smem = (size_t)(G - 1) * entity_comps(t->model) * tpg * VEC * sizeof(float);
+#define KGE_CASE(MM)                                                                       \
+  case MM:                                                                                 \
+    if (mode == KGE_HEAD_BATCH)                                                            \
+      return vec ? launch_bwd<MM, true, 4>(p, grid, smem, st) : launch_bwd<MM, true, 1>(p, grid, smem, st); \
+    return vec ? launch_bwd<MM, false, 4>(p, grid, smem, st) : launch_bwd<MM, false, 1>(p, grid, smem, st);
+  switch (t->model) {
+    KGE_CASE(KGE_TRANSE)
+    KGE_CASE(KGE_DISTMULT)
+    KGE_CASE(KGE_COMPLEX)
+    KGE_CASE(KGE_ROTATE)
+  }
+#undef KGE_CASE
+  return KGE_E_MODEL;
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_score_fwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
+                             const int64_t* neg, int64_t K, float* scores, kge_stream_t stream) {
+  int rc = validate_tables(t);
+  if (rc) return rc;
+  if (!sample || !scores) return KGE_E_NULL;
+  if (B < 0 || B > INT32_MAX || (neg && (K <= 0 || K > INT32_MAX))) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  if (B == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdParams p{};
+  fill_fwd(p, t);
+  p.sample = sample;
+  p.B = (int)B;
+  const bool vec = can_vectorize(t);
+  if (!neg) {
+    p.pos_score = scores;
+    p.K = 0;
+    const unsigned grid = (unsigned)((B + kWarps - 1) / kWarps);
+#define KGE_CASE(MM)                                                        \
+  case MM:                                                                  \
+    if (vec) score_pos_kernel<MM, 4><<<grid, kThreads, 0, st>>>(p);         \
+    else score_pos_kernel<MM, 1><<<grid, kThreads, 0, st>>>(p);             \
+    break;
+    switch (t->model) {
+      KGE_CASE(KGE_TRANSE)
+      KGE_CASE(KGE_DISTMULT)
+      KGE_CASE(KGE_COMPLEX)
+      KGE_CASE(KGE_ROTATE)
+    }
+#undef KGE_CASE
+    KGE_LAUNCH_CHECK();
+    return KGE_OK;
+  }
+  p.neg = neg;
+  p.neg_score = scores;
+  p.K = (int)K;
+  const int want = (4 * sm_count() + (int)B - 1) / (int)B;
+  const int maxks = (p.K + 63) / 64;
+  int ks = want < 1 ? 1 : (want > maxks ? maxks : want);
+  p.k_per_cta = (p.K + ks - 1) / ks;
+  ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
+  const size_t smem = (size_t)entity_comps(t->model) * p.Dp * sizeof(float);
+  return dispatch_neg<false>(t->model, mode, vec, p, dim3((unsigned)B, (unsigned)ks), smem, st);
+}
+
+extern "C" int kge_score_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
+                             const int64_t* neg, int64_t K, const float* grad_scores, float* grad_entity,
+                             float* grad_relation, kge_stream_t stream) {
+  int rc = validate_tables(t);
+  if (rc) return rc;
+  if (!sample || !grad_scores || !grad_entity || !grad_relation) return KGE_E_NULL;
+  if (B < 0 || B > INT32_MAX || (neg && (K <= 0 || K > INT32_MAX))) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  if (B == 0) return KGE_OK;
+  if (!neg)
+    return run_bwd(t, KGE_TAIL_BATCH, sample, B, nullptr, 0, grad_scores, nullptr, nullptr, nullptr,
+                   grad_entity, grad_relation, (cudaStream_t)stream);
+  return run_bwd(t, mode, sample, B, neg, K, nullptr, grad_scores, nullptr, nullptr, grad_entity,
+                 grad_relation, (cudaStream_t)stream);
+}
+
+extern "C" size_t kge_loss_workspace_bytes(int64_t B) {
+  return (size_t)(3 * (B > 0 ? B : 0)) * sizeof(float) + 16;
+}
+
+extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
+                             const int64_t* neg, int64_t K, const float* weight, float alpha,
+                             float* pos_score, float* neg_score, float* coef_pos, float* coef_neg,
+                             float* stats, void* workspace, kge_stream_t stream) {
+  int rc = validate_tables(t);
+  if (rc) return rc;
+  if (!sample || !neg || !weight || !coef_pos || !coef_neg || !stats || !workspace) return KGE_E_NULL;
+  if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  FwdParams p{};
+  fill_fwd(p, t);
+  p.sample = sample;
+  p.neg = neg;
+  p.weight = weight;
+  p.pos_score = pos_score;
+  p.neg_score = neg_score;
+  p.coef_pos = coef_pos;
+  p.coef_neg = coef_neg;
+  p.stats = stats;
+  p.ticket = reinterpret_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 16);
+  p.B = (int)B;
+  p.K = (int)K;
+  p.k_per_cta = (int)K;
+  p.alpha = alpha;
+  const size_t smem = ((size_t)entity_comps(t->model) * p.Dp + (size_t)K) * sizeof(float);
+  if (smem > 200 * 1024) return KGE_E_UNSUPPORTED;
+  return dispatch_neg<true>(t->model, mode, can_vectorize(t), p, dim3((unsigned)B, 1), smem,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int kge_fused_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
+                             const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
+                             const float* stats, const float* grad_loss, float* grad_entity,
+                             float* grad_relation, kge_stream_t stream) {
+  int rc = validate_tables(t);
+  if (rc) return rc;
+  if (!sample || !neg || !coef_pos || !coef_neg || !stats || !grad_entity || !grad_relation)
+    return KGE_E_NULL;
+  if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, grad_entity,
+                 grad_relation, (cudaStream_t)stream);
+}

@@ -1,0 +1,3 @@
+from .dataset import Dataset, from_directory
+
+__all__ = ["Dataset", "from_directory"]

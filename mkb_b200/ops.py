@@ -1,0 +1,357 @@
+"""Thin tensor-level wrappers over the C ABI and the autograd glue around them.
+
+Nothing here computes: every function validates devices/dtypes, allocates outputs with torch and
+launches one kernel of libkge_b200.so on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+__all__ = [
+    "score", "adversarial_loss", "fused_adversarial_step", "sample_negatives", "filter_pool",
+    "rank_all", "adam_step", "FilterCSR", "TableSpec",
+]
+
+
+class TableSpec:
+    """The constants of a model that the kernels need, detached from nn.Module."""
+
+    def __init__(self, model_name, hidden_dim, gamma, embedding_range):
+        self.model_name = model_name
+        self.model_id = N.MODEL_IDS[model_name]
+        self.hidden_dim = int(hidden_dim)
+        self.gamma = float(gamma)
+        self.embedding_range = float(embedding_range)
+
+    def struct(self, ent, rel):
+        nc = 2 if self.model_name in ("ComplEx", "RotatE") else 1
+        rc = 2 if self.model_name == "ComplEx" else 1
+        if ent.shape[1] != nc * self.hidden_dim or rel.shape[1] != rc * self.hidden_dim:
+            raise ValueError(
+                f"{self.model_name}: table shapes {tuple(ent.shape)}/{tuple(rel.shape)} do not match "
+                f"hidden_dim={self.hidden_dim}")
+        return N.KgeTables(ent.data_ptr(), rel.data_ptr(), ent.shape[0], rel.shape[0], self.hidden_dim,
+                           self.model_id, self.gamma, self.embedding_range)
+
+
+def _mode_id(mode):
+    if mode == "head-batch":
+        return N.HEAD_BATCH
+    if mode in ("tail-batch", None):
+        return N.TAIL_BATCH
+    raise ValueError(f"unknown mode {mode!r}")
+
+
+def _prep_tables(ent, rel):
+    N.require_cuda(ent, rel)
+    if ent.dtype != torch.float32 or rel.dtype != torch.float32:
+        raise TypeError("embedding tables must be float32")
+    return ent.contiguous(), rel.contiguous()
+
+
+def _prep_ids(t, device):
+    if t is None:
+        return None
+    N.require_cuda(t)
+    return t.to(device=device, dtype=torch.int64).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 score (+ autograd)
+# ---------------------------------------------------------------------------------------------
+def _score_fwd(spec, ent, rel, sample, neg, mode):
+    lib = N.load()
+    B = sample.shape[0]
+    K = 1 if neg is None else neg.shape[1]
+    out = torch.empty((B, K), dtype=torch.float32, device=ent.device)
+    tb = spec.struct(ent, rel)
+    N.check(lib.kge_score_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg),
+                              0 if neg is None else K, N.ptr(out), N.stream_ptr(ent.device)),
+            "kge_score_fwd")
+    N.count_launch()
+    return out
+
+
+class _ScoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ent, rel, sample, neg, mode, spec):
+        ent_c, rel_c = _prep_tables(ent, rel)
+        ctx.save_for_backward(ent_c, rel_c, sample, neg)
+        ctx.mode, ctx.spec = mode, spec
+        with torch.cuda.device(ent.device):
+            return _score_fwd(spec, ent_c, rel_c, sample, neg, mode)
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        ent, rel, sample, neg = ctx.saved_tensors
+        lib = N.load()
+        g = grad_scores.contiguous().float()
+        # index_select's backward yields dense gradients: same contract here
+        g_ent = torch.zeros_like(ent)
+        g_rel = torch.zeros_like(rel)
+        tb = ctx.spec.struct(ent, rel)
+        B = sample.shape[0]
+        with torch.cuda.device(ent.device):
+            N.check(lib.kge_score_bwd(C.byref(tb), _mode_id(ctx.mode), N.ptr(sample), B, N.ptr(neg),
+                                      0 if neg is None else neg.shape[1], N.ptr(g), N.ptr(g_ent),
+                                      N.ptr(g_rel), N.stream_ptr(ent.device)), "kge_score_bwd")
+        N.count_launch()
+        return g_ent, g_rel, None, None, None, None
+
+
+def score(spec, ent, rel, sample, neg=None, mode=None):
+    """``model(sample[, negative_sample, mode])`` -> float32 ``[B,1]`` / ``[B,K]``, differentiable
+    w.r.t. both tables (mkb/models/base.py:153-207 + the model's forward)."""
+    N.require_cuda(ent, rel, sample, neg)
+    sample = _prep_ids(sample, ent.device)
+    neg = _prep_ids(neg, ent.device)
+    if neg is None:
+        mode = None
+    if sample.dim() != 2 or sample.shape[1] != 3:
+        raise ValueError("sample must be [B,3]")
+    if neg is not None and (neg.dim() != 2 or neg.shape[0] != sample.shape[0]):
+        raise ValueError("negative_sample must be [B,K]")
+    return _ScoreFn.apply(ent, rel, sample, neg, mode, spec)
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone adversarial loss (+ autograd)
+# ---------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _loss_workspace(B, device):
+    """Zero-initialised ticket + partials buffer, cached per (device, stream, B-bucket)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    need = N.load().kge_loss_workspace_bytes(B)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class _AdvLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, neg, weight, alpha):
+        lib = N.load()
+        pos_c = pos.contiguous().float().view(-1)
+        neg_c = neg.contiguous().float()
+        w_c = weight.contiguous().float().view(-1)
+        B, K = neg_c.shape
+        stats = torch.empty(4, dtype=torch.float32, device=neg_c.device)
+        with torch.cuda.device(neg_c.device):
+            ws = _loss_workspace(B, neg_c.device)
+            N.check(lib.kge_adv_loss_fwd(N.ptr(pos_c), N.ptr(neg_c), N.ptr(w_c), B, K, alpha, N.ptr(stats),
+                                         N.ptr(ws), N.stream_ptr(neg_c.device)), "kge_adv_loss_fwd")
+        N.count_launch()
+        ctx.save_for_backward(pos_c, neg_c, w_c, stats)
+        ctx.alpha, ctx.pos_shape = alpha, pos.shape
+        return stats[3].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        pos, neg, w, stats = ctx.saved_tensors
+        lib = N.load()
+        B, K = neg.shape
+        gpos = torch.empty_like(pos)
+        gneg = torch.empty_like(neg)
+        gl = grad_loss.contiguous().float()
+        with torch.cuda.device(neg.device):
+            N.check(lib.kge_adv_loss_bwd(N.ptr(pos), N.ptr(neg), N.ptr(w), B, K, ctx.alpha, N.ptr(stats),
+                                         N.ptr(gl), N.ptr(gpos), N.ptr(gneg), N.stream_ptr(neg.device)),
+                    "kge_adv_loss_bwd")
+        N.count_launch()
+        return gpos.view(ctx.pos_shape), gneg, None, None
+
+
+def adversarial_loss(pos, neg, weight, alpha=0.5):
+    """losses.Adversarial.__call__ (mkb/losses/adversarial.py:21-30) as one kernel."""
+    N.require_cuda(pos, neg, weight)
+    return _AdvLossFn.apply(pos, neg, weight, float(alpha))
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 + K3: the fused training step
+# ---------------------------------------------------------------------------------------------
+class _FusedStepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ent, rel, sample, neg, weight, mode, alpha, spec, want_scores):
+        lib = N.load()
+        ent_c, rel_c = _prep_tables(ent, rel)
+        B, K = neg.shape
+        dev = ent.device
+        coef_pos = torch.empty(B, dtype=torch.float32, device=dev)
+        coef_neg = torch.empty((B, K), dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        pos_s = torch.empty((B, 1), dtype=torch.float32, device=dev) if want_scores else None
+        neg_s = torch.empty((B, K), dtype=torch.float32, device=dev) if want_scores else None
+        tb = spec.struct(ent_c, rel_c)
+        with torch.cuda.device(dev):
+            ws = _loss_workspace(B, dev)
+            N.check(lib.kge_fused_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K,
+                                      N.ptr(weight), alpha, N.ptr(pos_s), N.ptr(neg_s), N.ptr(coef_pos),
+                                      N.ptr(coef_neg), N.ptr(stats), N.ptr(ws), N.stream_ptr(dev)),
+                    "kge_fused_fwd")
+        N.count_launch()
+        ctx.save_for_backward(ent_c, rel_c, sample, neg, coef_pos, coef_neg, stats)
+        ctx.mode, ctx.spec = mode, spec
+        loss = stats[3].clone()
+        if want_scores:
+            ctx.mark_non_differentiable(pos_s, neg_s)
+            return loss, pos_s, neg_s
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss, *_):
+        ent, rel, sample, neg, coef_pos, coef_neg, stats = ctx.saved_tensors
+        lib = N.load()
+        g_ent = torch.zeros_like(ent)
+        g_rel = torch.zeros_like(rel)
+        gl = grad_loss.contiguous().float()
+        tb = ctx.spec.struct(ent, rel)
+        B, K = neg.shape
+        with torch.cuda.device(ent.device):
+            N.check(lib.kge_fused_bwd(C.byref(tb), _mode_id(ctx.mode), N.ptr(sample), B, N.ptr(neg), K,
+                                      N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats), N.ptr(gl),
+                                      N.ptr(g_ent), N.ptr(g_rel), N.stream_ptr(ent.device)),
+                    "kge_fused_bwd")
+        N.count_launch()
+        return g_ent, g_rel, None, None, None, None, None, None, None
+
+
+def fused_adversarial_step(spec, ent, rel, sample, neg, weight, mode, alpha=0.5, return_scores=False):
+    """``loss(model(sample), model(sample, neg, mode), weight)`` (mkb/compose/pipeline.py:211-234) as
+    ONE forward kernel; ``.backward()`` on the result launches ONE backward kernel."""
+    N.require_cuda(ent, rel, sample, neg, weight)
+    if mode not in ("head-batch", "tail-batch"):
+        raise ValueError(f"unknown mode {mode!r}")
+    sample = _prep_ids(sample, ent.device)
+    neg = _prep_ids(neg, ent.device)
+    weight = weight.to(device=ent.device, dtype=torch.float32).contiguous().view(-1)
+    if neg.dim() != 2 or neg.shape[0] != sample.shape[0] or weight.shape[0] != sample.shape[0]:
+        raise ValueError("shape mismatch between sample, negative_sample and weight")
+    return _FusedStepFn.apply(ent, rel, sample, neg, weight, mode, float(alpha), spec, bool(return_scores))
+
+
+def fused_forward_raw(spec, ent, rel, sample, neg, weight, mode, alpha, coef_pos, coef_neg, stats, ws,
+                      pos_score=None, neg_score=None):
+    """Autograd-free K2 launch into caller-owned buffers (the device-resident training loop)."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    B, K = neg.shape
+    N.check(lib.kge_fused_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K, N.ptr(weight),
+                              alpha, N.ptr(pos_score), N.ptr(neg_score), N.ptr(coef_pos), N.ptr(coef_neg),
+                              N.ptr(stats), N.ptr(ws), N.stream_ptr(ent.device)), "kge_fused_fwd")
+    N.count_launch()
+
+
+def fused_backward_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, g_ent, g_rel,
+                       grad_loss=None):
+    """Autograd-free K3 launch: ADDS into g_ent / g_rel."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    B, K = neg.shape
+    N.check(lib.kge_fused_bwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K, N.ptr(coef_pos),
+                              N.ptr(coef_neg), N.ptr(stats), N.ptr(grad_loss), N.ptr(g_ent), N.ptr(g_rel),
+                              N.stream_ptr(ent.device)), "kge_fused_bwd")
+    N.count_launch()
+
+
+# ---------------------------------------------------------------------------------------------
+# K4 sampler
+# ---------------------------------------------------------------------------------------------
+class FilterCSR:
+    """Device-resident true-entity sets (mkb/sampling/negative_sampling.py:7-28 as a CSR)."""
+
+    def __init__(self, keys, offsets, members):
+        self.keys, self.offsets, self.members = keys, offsets, members
+
+    @property
+    def device(self):
+        return self.keys.device
+
+    def to(self, device):
+        if self.keys.device == torch.device(device):
+            return self
+        return FilterCSR(self.keys.to(device), self.offsets.to(device), self.members.to(device))
+
+    def struct(self):
+        return N.KgeFilterCsr(self.keys.data_ptr(), self.offsets.data_ptr(), self.members.data_ptr(),
+                              self.keys.shape[0])
+
+
+def sample_negatives(csr, sample, mode, size, n_entity, seed, offset, status=None, out=None):
+    lib = N.load()
+    N.require_cuda(sample, csr.keys)
+    B = sample.shape[0]
+    dev = sample.device
+    if out is None:
+        out = torch.empty((B, size), dtype=torch.int64, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    fs = csr.struct()
+    with torch.cuda.device(dev):
+        N.check(lib.kge_sample_negatives(C.byref(fs), _mode_id(mode), N.ptr(sample), B, size, n_entity,
+                                         C.c_uint64(seed & (2**64 - 1)), C.c_uint64(offset), N.ptr(out),
+                                         N.ptr(status), N.stream_ptr(dev)), "kge_sample_negatives")
+    N.count_launch()
+    return out, status
+
+
+def filter_pool(csr, sample, mode, size, n_entity, pool, status=None, out=None):
+    lib = N.load()
+    N.require_cuda(sample, csr.keys, pool)
+    B = sample.shape[0]
+    dev = sample.device
+    if out is None:
+        out = torch.empty((B, size), dtype=torch.int64, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    fs = csr.struct()
+    with torch.cuda.device(dev):
+        N.check(lib.kge_filter_pool(C.byref(fs), _mode_id(mode), N.ptr(sample), B, size, n_entity,
+                                    N.ptr(pool), pool.shape[0], N.ptr(out), N.ptr(status),
+                                    N.stream_ptr(dev)), "kge_filter_pool")
+    N.count_launch()
+    return out, status
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 ranking
+# ---------------------------------------------------------------------------------------------
+def rank_all(spec, ent, rel, queries, mode, csr=None, return_scores=False):
+    """Filtered rank of the true entity for every query (int64 ``[Q]``)."""
+    lib = N.load()
+    ent, rel = _prep_tables(ent.detach(), rel.detach())
+    queries = _prep_ids(queries, ent.device)
+    Q = queries.shape[0]
+    dev = ent.device
+    ranks = torch.empty(Q, dtype=torch.int64, device=dev)
+    scores = torch.empty((Q, ent.shape[0]), dtype=torch.float32, device=dev) if return_scores else None
+    tb = spec.struct(ent, rel)
+    ws = torch.empty(max(lib.kge_rank_workspace_bytes(C.byref(tb), Q), 8), dtype=torch.uint8, device=dev)
+    fs = csr.to(dev).struct() if csr is not None else None
+    with torch.cuda.device(dev):
+        N.check(lib.kge_rank_all(C.byref(tb), _mode_id(mode), N.ptr(queries), Q,
+                                 C.byref(fs) if fs is not None else None, N.ptr(ranks), N.ptr(scores),
+                                 N.ptr(ws), N.stream_ptr(dev)), "kge_rank_all")
+    N.count_launch(2)
+    return (ranks, scores) if return_scores else ranks
+
+
+# ---------------------------------------------------------------------------------------------
+# dense Adam
+# ---------------------------------------------------------------------------------------------
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=False):
+    lib = N.load()
+    N.require_cuda(param, grad, exp_avg, exp_avg_sq)
+    with torch.cuda.device(param.device):
+        N.check(lib.kge_adam_step(N.ptr(param), N.ptr(grad), N.ptr(exp_avg), N.ptr(exp_avg_sq), param.numel(),
+                                  int(step), lr, beta1, beta2, eps, int(bool(zero_grad)),
+                                  N.stream_ptr(param.device)), "kge_adam_step")
+    N.count_launch()

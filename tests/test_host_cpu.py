@@ -1,0 +1,133 @@
+"""CPU tests: host-side logic, ABI surface, fail-loud behaviour.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import kge_oracle as ko
+
+import mkb_b200
+from mkb_b200 import _native, datasets, models, sampling
+from mkb_b200.utils import build_filter_csr
+
+
+def test_library_exports_every_declared_symbol():
+    """include/kge_b200.h <-> libkge_b200.so <-> the ctypes prototypes agree symbol by symbol."""
+    header = open(os.path.join(ROOT, "include", "kge_b200.h")).read()
+    declared = set(re.findall(r"\b(kge_[a-z_0-9]+)\s*\(", header))
+    declared -= {"kge_filter_csr", "kge_tables"}
+    assert len(declared) >= 15
+    lib = _native.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+    assert lib.kge_abi_version() == 1
+    assert b"NULL" in lib.kge_strerror(-1)
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_native.KgeTables) == 48
+    assert ctypes.sizeof(_native.KgeFilterCsr) == 32
+    assert _native.KgeTables.hidden_dim.offset == 32 and _native.KgeTables.gamma.offset == 40
+
+
+def test_argument_validation_without_gpu():
+    lib = _native.load()
+    t = _native.KgeTables(None, None, 10, 2, 4, 0, 1.0, 0.5)
+    assert lib.kge_score_fwd(ctypes.byref(t), 0, None, 1, None, 0, None, None) == -1  # NULL tables
+    t = _native.KgeTables(16, 16, 10, 2, 4, 9, 1.0, 0.5)
+    assert lib.kge_score_fwd(ctypes.byref(t), 0, 16, 1, None, 0, 16, None) == -3  # bad model
+    t = _native.KgeTables(16, 16, 10, 2, 4, 0, 1.0, 0.5)
+    assert lib.kge_score_fwd(ctypes.byref(t), 7, 16, 1, None, 0, 16, None) == -4  # bad mode
+    assert lib.kge_adam_step(None, None, None, None, 4, 1, 0.1, 0.9, 0.999, 1e-8, 0, None) == -1
+    assert lib.kge_loss_workspace_bytes(1024) == 3 * 1024 * 4 + 16
+
+
+def test_model_init_matches_reference_under_seed(eval_doctest):
+    """Same parameter creation order and init calls as mkb/models/base.py:86-100 => identical tables
+    for a given torch seed (the doctest constructs Dataset(seed=42) first, then the model)."""
+    g = eval_doctest
+    torch.manual_seed(42)
+    train = [(0, 0, 1), (0, 1, 1), (2, 0, 3), (2, 1, 3)]
+    entities = {"e0": 0, "e1": 1, "e2": 2, "e3": 3}
+    relations = {"r0": 0, "r1": 1}
+    ds = datasets.Dataset(train=train, valid=train[:1], test=train[:1], entities=entities, relations=relations,
+                          batch_size=2, seed=42, shuffle=False)
+    m = models.RotatE(hidden_dim=3, entities=ds.entities, relations=ds.relations, gamma=1)
+    np.testing.assert_array_equal(m.entity_embedding.detach().numpy(), g["ent0"])
+    np.testing.assert_array_equal(m.relation_embedding.detach().numpy(), g["rel0"])
+    assert m.entity_dim == 6 and m.relation_dim == 3 and m.modulus.shape == (1, 1)
+    assert [n for n, p in m.named_parameters() if p.requires_grad] == [
+        "entity_embedding", "relation_embedding", "modulus"]
+    # the batches the doctest's loop saw
+    for step, data in enumerate(ds):
+        np.testing.assert_array_equal(data["sample"].numpy(), g[f"step{step}/sample"])
+        np.testing.assert_allclose(data["weight"].numpy(), g[f"step{step}/weight"], rtol=1e-7)
+        assert data["mode"] == str(g[f"step{step}/mode"])
+
+
+def test_dimensions_and_repr():
+    e, r = {i: i for i in range(5)}, {i: i for i in range(2)}
+    assert models.TransE(4, e, r, 6).entity_embedding.shape == (5, 4)
+    assert models.DistMult(4, e, r, 6).relation_embedding.shape == (2, 4)
+    cx = models.ComplEx(4, e, r, 6)
+    assert cx.entity_embedding.shape == (5, 8) and cx.relation_embedding.shape == (2, 8)
+    assert "ComplEx model" in repr(cx)
+    assert abs(cx.embedding_range.item() - 2.0) < 1e-7
+    emb = cx.embeddings
+    assert set(emb) == {"entities", "relations"} and len(emb["entities"]) == 5
+    s, shape = cx.format_sample(torch.zeros(2, 3, 3, dtype=torch.long))
+    assert s.shape == (6, 3) and shape == (2, 3)
+
+
+def test_cpu_call_fails_loudly():
+    m = models.TransE(4, {0: 0, 1: 1}, {0: 0}, 3)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.tensor([[0, 0, 1]]))
+    if not torch.cuda.is_available():
+        ns = sampling.NegativeSampling(2, [(0, 0, 1)], {0: 0, 1: 1}, {0: 0})
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns.generate(torch.tensor([[0, 0, 1]]), "tail-batch")
+
+
+def test_filter_csr_matches_oracle(sampler_cases):
+    g = sampler_cases
+    triples = [tuple(int(x) for x in r) for r in g["triples"]]
+    for side in ("head", "tail"):
+        a = build_filter_csr(triples, int(g["N"]), side)
+        b = ko.build_filter_csr(triples, int(g["N"]), side)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    ns = sampling.NegativeSampling(4, triples, range(int(g["N"])), range(int(g["R"])))
+    ref_keys = [tuple(int(x) for x in k) for k in g["true_head_keys"]]
+    assert set(ns.true_head) == set(ref_keys)
+    k0 = ref_keys[0]
+    np.testing.assert_array_equal(ns.true_head[k0], g["true_head_members"][: int(g["true_head_sizes"][0])])
+
+
+def test_dataset_weights_and_iteration(sampler_cases):
+    g = sampler_cases
+    triples = [tuple(int(x) for x in r) for r in g["triples"]]
+    ds = datasets.Dataset(train=triples, entities={i: i for i in range(60)}, relations={i: i for i in range(4)},
+                          batch_size=64, shuffle=True, seed=42)
+    np.testing.assert_allclose(ds._weights.numpy(), g["weights"], rtol=1e-7)
+    batches = list(ds)
+    assert len(batches) == 2 * -(-400 // 64) and len(ds) == int(800 / 64)
+    assert [b["mode"] for b in batches[:4]] == ["head-batch", "tail-batch", "head-batch", "tail-batch"]
+    assert batches[-1]["sample"].shape == (400 % 64, 3)
+    seen = torch.cat([b["sample"] for b in batches[0::2]])
+    assert sorted(map(tuple, seen.tolist())) == sorted(triples)  # one epoch visits every triple once
+    nxt = next(ds)
+    assert nxt["mode"] == "tail-batch" and next(ds)["mode"] == "head-batch"
+
+
+def test_dataset_builds_mappings_like_reference():
+    train = [("mkb", "is_a", "library"), ("github", "is_a", "tool"), ("mkb", "is_on", "github")]
+    ds = datasets.Dataset(train=train, batch_size=1, shuffle=False)
+    assert ds.entities == {"mkb": 0, "github": 1, "library": 2, "tool": 3}
+    assert ds.relations == {"is_a": 0, "is_on": 1}
+    assert ds.train == [(0, 0, 2), (1, 0, 3), (0, 1, 1)]
