@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — training triples/s of the fused KGE step (BASELINE.json's metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2]
+
+Own arm ("ours"): one step = negative sampling -> fused gather/score/adversarial-loss forward ->
+fused atomic-scatter backward -> dense Adam on both tables (gradient zeroing folded in), i.e. the
+loop body of mkb/compose/pipeline.py:206-242, on a synthetic batch of the named config.
+  * value : whole-job triples/s (positives + negatives scored = B*(1+K) per step per GPU) with the
+            step's inputs already in HBM, timed with CUDA events over exactly K steps, max over ranks;
+  * e2e   : the same step driven through the public API (ops.fused_adversarial_step + autograd +
+            optim.DenseAdam, what compose.Pipeline.learn runs) from PINNED HOST batches, host->device
+            copies and the loss read-back inside the timed region;
+  * roofline : the dominant kernel (fused backward), algorithmic bytes / CUDA-event time measured
+            inside the timed region vs the measured HBM peak in MEASURED_PEAKS.json;
+  * cpu_baseline : the reference's eager-PyTorch CPU operator sequence (oracle/torch_port.py, bit-exact
+            with the reference on the golden vectors) timed on this box's host cores on a bounded
+            sample of the same workload (rank 0, N=1 only).
+
+Reference arm (--impl reference): that same CPU port, all host threads, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# name: (dataset label, model, n_entity, n_relation, n_train, hidden_dim, batch, negatives, gamma)
+CONFIGS = {
+    "cfg1": ("Wn18rr", "TransE", 40943, 11, 86835, 200, 256, 64, 6.0),
+    "cfg2": ("FB15k-237", "RotatE", 14541, 237, 272115, 1000, 1024, 256, 9.0),
+    "cfg3": ("FB15k-237", "ComplEx", 14541, 237, 272115, 1000, 1024, 256, 9.0),
+    "cfg4": ("Yago3-10", "RotatE", 123182, 37, 1079040, 500, 1024, 256, 24.0),
+}
+METRIC = "training triples/sec (pos+neg scored)"
+UNIT = "triples/s"
+
+
+def workload_name(cfg):
+    ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    return f"{ds}-shaped synthetic graph, {model} dim={D} batch={B} neg={K} Adversarial+Adam ({cfg})"
+
+
+def synth_graph(cfg, seed=41):
+    """Seeded synthetic triples with the named dataset's entity/relation/train counts."""
+    _, _, N, R, T, *_ = CONFIGS[cfg]
+    rng = np.random.RandomState(seed)
+    tri = np.stack([rng.randint(N, size=T), rng.randint(R, size=T), rng.randint(N, size=T)], 1).astype(np.int64)
+    return np.unique(tri, axis=0)
+
+
+def row_bytes(model, D):
+    row_e = 4 * D * (2 if model in ("ComplEx", "RotatE") else 1)
+    row_r = 4 * D * (2 if model == "ComplEx" else 1)
+    return row_e, row_r
+
+
+def algorithmic_bytes(cfg):
+    """logical gather bytes, every row counted once per use, fp32 tables, int64 ids."""
+    _, model, N, R, T, D, B, K, _ = CONFIGS[cfg]
+    row_e, row_r = row_bytes(model, D)
+    fwd = B * (2 * row_e + row_r) + B * K * row_e + 8 * (3 * B + B * K) + 4 * B + 4 * B * (1 + K) + 4
+    bwd = fwd + B * K * row_e + 2 * B * row_e + B * row_r  # re-read (recompute) + atomic row writes
+    return fwd, bwd
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap"}
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = torch.cuda.get_device_properties(device_index).uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}".encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[device_index]) if vis else device_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's eager-PyTorch CPU path (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, steps, warmup, budget_s, graph=None):
+    """Times oracle/torch_port.CpuTrainer (loop body of compose/pipeline.py:206-242: reference sampler,
+    two forwards, loss, backward, dense Adam) on a bounded sample: the first B_s positives of each
+    batch with all K negatives, B_s chosen so (steps+warmup) steps fit in ``budget_s`` seconds."""
+    from oracle import torch_port as tp
+
+    ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    cores = torch.get_num_threads()
+    graph = synth_graph(cfg) if graph is None else graph
+    tri = [tuple(r) for r in graph.tolist()]
+    th, tt = tp.true_sets(tri)
+    trainer = tp.CpuTrainer(model, N, R, D, gamma, lr=5e-5, seed=42)
+    rng = np.random.RandomState(42)
+    pick = np.random.RandomState(1)
+
+    def batch(bs):
+        idx = pick.choice(len(tri), bs, replace=False)
+        return torch.tensor([tri[i] for i in idx]), torch.full((bs,), 0.3)
+
+    def one(bs, mode):
+        s, w = batch(bs)
+        t0 = time.perf_counter()
+        neg = tp.generate_negatives(rng, s, mode, th, tt, N, K)
+        trainer.step(s, w, mode, neg)
+        return time.perf_counter() - t0
+
+    one(2, "tail-batch")  # first-touch of the allocator / thread pool
+    t_probe = one(4, "head-batch") / 4  # seconds per positive row
+    bs = int(max(2, min(B, budget_s / max(steps + warmup, 1) / max(t_probe, 1e-6))))
+    for i in range(warmup):
+        one(bs, "head-batch" if i % 2 == 0 else "tail-batch")
+    t = 0.0
+    for i in range(steps):
+        t += one(bs, "head-batch" if i % 2 == 0 else "tail-batch")
+    value = bs * (1 + K) * steps / t
+    return {
+        "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{steps} steps x first {bs} of {B} positives per batch, all {K} negatives each, D={D}: "
+                  f"reference sampler + 2 forwards + loss + backward + dense Adam (oracle/torch_port.py, "
+                  f"torch {torch.__version__} CPU, {cores} threads)",
+        "ms_per_step": 1e3 * t / steps,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = args.config
+    base = cpu_reference_run(cfg, args.steps, args.warmup, budget_s=150.0)
+    ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "device": "cpu"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from mkb_b200 import _native, models, ops, optim, sampling
+    from mkb_b200.compose import DeviceTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = world > 1
+    if dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"# warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+
+    cfg = args.config
+    ds, mname, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    graph = synth_graph(cfg)
+
+    torch.manual_seed(42)  # identical replicas on every rank
+    model = getattr(models, mname)(hidden_dim=D, entities={i: i for i in range(N)},
+                                   relations={i: i for i in range(R)}, gamma=gamma).to(dev)
+    ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
+                                   seed=42 + rank, device=dev)
+    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist)
+
+    # this rank's batches: disjoint slices of a seeded permutation of the training triples
+    from mkb_b200.datasets.dataset import subsampling_weights
+
+    weights_all = subsampling_weights(graph)
+    perm = np.random.RandomState(43).permutation(len(graph))
+    n_batches = steps + warmup
+    need = n_batches * B * world
+    reps = -(-need // len(perm))
+    order = np.tile(perm, reps)[:need].reshape(n_batches, world, B)[:, rank, :]
+    host_samples = torch.from_numpy(graph[order]).pin_memory()  # [n_batches, B, 3]
+    host_weights = weights_all[torch.from_numpy(order)].pin_memory()
+    dev_samples = host_samples.to(dev)
+    dev_weights = host_weights.to(dev)
+    modes = ["head-batch" if i % 2 == 0 else "tail-batch" for i in range(n_batches)]
+
+    def barrier():
+        if dist:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (value) ----------------
+    for i in range(warmup):
+        trainer.step(dev_samples[i], dev_weights[i], modes[i])
+    ns.check_status(dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _native.launches
+    barrier()
+    with ClockSampler(local) as clocks:
+        t0.record()
+        for i in range(steps):
+            trainer.hooks = ev[i]
+            trainer.step(dev_samples[warmup + i], dev_weights[warmup + i], modes[warmup + i])
+        t1.record()
+        barrier()
+    trainer.hooks = None
+    launches = _native.launches - launches0
+    ms_total = t0.elapsed_time(t1)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    final_loss = trainer.loss()
+    ns.check_status(dev)
+
+    # ---------------- end-to-end arm through the public API, host batches ----------------
+    torch.manual_seed(42)
+    model2 = getattr(models, mname)(hidden_dim=D, entities={i: i for i in range(N)},
+                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
+    opt = optim.DenseAdam(filter(lambda p: p.requires_grad, model2.parameters()), lr=5e-5)
+
+    def e2e_step(i):
+        s = host_samples[i].to(dev, non_blocking=True)
+        w = host_weights[i].to(dev, non_blocking=True)
+        neg = ns.generate(s, modes[i])
+        err = ops.fused_adversarial_step(model2.spec, model2.entity_embedding, model2.relation_embedding, s, neg,
+                                         w, modes[i], 0.5)
+        err.backward()
+        if dist:
+            for p in (model2.entity_embedding, model2.relation_embedding):
+                torch.distributed.all_reduce(p.grad)
+        opt.step()
+        opt.zero_grad()
+        return err.item()  # the reference's per-step loss read-back (pipeline.py:242)
+
+    for i in range(warmup):
+        e2e_step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        e2e_step(warmup + i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+    if dist:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total, e2e_ms, fwd_ms, bwd_ms = t.tolist()
+    triples_per_step = B * (1 + K) * world
+    value = triples_per_step * steps / (ms_total * 1e-3)
+    e2e_value = triples_per_step * steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        fwd_b, bwd_b = algorithmic_bytes(cfg)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[cfg]["bwd_dram_bytes"]
+        except Exception:
+            pass
+        bwd_gbs = bwd_b / (bwd_ms * 1e-3) / 1e9
+        fwd_gbs = fwd_b / (fwd_ms * 1e-3) / 1e9
+        row_e, row_r = row_bytes(mname, D)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(cfg), "global_batch": B * world, "negatives": K,
+                "parallelism": f"dp{world}: replicated tables, all-reduce of 3 loss sums + dense grads" if dist else "single GPU",
+                "l2": "working set per step (tables+grads+Adam moments = "
+                      f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
+                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)",
+                "final_loss": final_loss,
+            },
+            "roofline": {
+                "kernel": "score_bwd_kernel (fused backward, K3)", "bound": "hbm", "achieved": bwd_gbs, "peak": hbm,
+                "unit": "GB/s", "frac": bwd_gbs / hbm, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bwd_b, "avg_launch_ms": bwd_ms,
+                "also": {"kernel": "score_neg_kernel<FUSED> (fused forward, K2)", "achieved": fwd_gbs,
+                         "frac": fwd_gbs / hbm, "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": fwd_ms},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps,
+                    "api": "sampling.generate + ops.fused_adversarial_step + backward + optim.DenseAdam + loss.item()"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_reference_run(cfg, steps=3, warmup=1, budget_s=20.0, graph=graph)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if dist:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,3 +1,4 @@
 from .pipeline import Pipeline
+from .trainer import DeviceTrainer
 
-__all__ = ["Pipeline"]
+__all__ = ["Pipeline", "DeviceTrainer"]

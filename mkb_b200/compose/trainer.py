@@ -1,0 +1,95 @@
+"""Device-resident training step: sampler -> fused forward -> fused backward -> dense Adam, five
+kernel launches on one stream, no host synchronisation and no allocation per step.
+
+This is the loop body of mkb/compose/pipeline.py:206-242 with every tensor the step touches kept in
+HBM (tables, gradients, Adam moments, the batch's negatives, per-score coefficients).  It is what
+``Pipeline.learn`` reduces to when nothing on the step needs the host, and what ``bench.py`` times.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): tables are replicated, each rank scores
+its own positives; the three loss sums are all-reduced between forward and backward so every rank
+normalises by the global sum of weights (losses/adversarial.py:28-30 over the global batch), and the
+dense gradients are all-reduced before the (replicated) Adam step.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+__all__ = ["DeviceTrainer"]
+
+
+class DeviceTrainer:
+    def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
+                 process_group=None, distributed=False):
+        ent, rel = model.entity_embedding, model.relation_embedding
+        if not ent.is_cuda:
+            raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
+        self.model, self.sampling = model, sampling
+        self.spec = model.spec
+        self.ent, self.rel = ent.data, rel.data
+        self.dev = ent.device
+        self.lr, self.betas, self.eps, self.alpha = lr, betas, eps, alpha
+        self.distributed = distributed
+        self.group = process_group
+        K = sampling.size
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        # one flat buffer for both gradients => a single all-reduce in the multi-GPU path
+        self._gflat = torch.zeros(self.ent.numel() + self.rel.numel(), **f32)
+        self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
+        self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
+        self.m_ent, self.v_ent = torch.zeros_like(self.ent), torch.zeros_like(self.ent)
+        self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
+        self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
+        self.coef_pos = torch.empty(max_batch, **f32)
+        self.coef_neg = torch.empty((max_batch, K), **f32)
+        self.stats = torch.zeros(4, **f32)
+        self.ws = torch.zeros(max(ops.N.load().kge_loss_workspace_bytes(max_batch), 64), dtype=torch.uint8,
+                              device=self.dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.max_batch, self.K = max_batch, K
+        self.t = 0
+        self._csr = {m: sampling._csr("head" if m == "head-batch" else "tail", self.dev)
+                     for m in ("head-batch", "tail-batch")}
+        self.hooks = None  # optional (pre_fwd, post_fwd, pre_bwd, post_bwd) event recorders for bench.py
+
+    launches_per_step = 5
+
+    def step(self, sample, weight, mode):
+        """One optimisation step on a device-resident batch; returns the device loss scalar (a view
+        of the stats buffer, valid until the next step)."""
+        B = sample.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        neg = self.neg[:B]
+        coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
+        s = self.sampling
+        ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg)
+        s._calls += 1
+        h = self.hooks
+        if h:
+            h[0].record()
+        ops.fused_forward_raw(self.spec, self.ent, self.rel, sample, neg, weight, mode, self.alpha, coef_pos,
+                              coef_neg, self.stats, self.ws)
+        if h:
+            h[1].record()
+        if self.distributed:
+            torch.distributed.all_reduce(self.stats[:3], group=self.group)
+        if h:
+            h[2].record()
+        ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
+                               self.g_ent, self.g_rel)
+        if h:
+            h[3].record()
+        if self.distributed:
+            torch.distributed.all_reduce(self._gflat, group=self.group)
+        self.t += 1
+        b1, b2 = self.betas
+        ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        return self.stats
+
+    def loss(self):
+        """Global loss of the last step (host float; synchronises)."""
+        s = self.stats
+        return float((-(s[0] + s[1]) / (2 * s[2])).item())

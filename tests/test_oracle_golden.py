@@ -45,6 +45,48 @@ def test_fp32_mode_tracks_reference_fp32(step_cases):
         np.testing.assert_allclose(s, g[f"{k}/f32/neg_score"], rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("mode", MODES)
+def test_torch_port_is_bit_exact(step_cases, model, mode):
+    """oracle/torch_port.py issues the reference's ATen operator sequence: on the same inputs its fp32
+    scores, loss and autograd gradients equal the reference's bit for bit (same torch build)."""
+    import torch
+
+    from oracle import torch_port as tp
+
+    g = step_cases
+    for D in (8, 5):
+        k = f"{model}_D{D}_{mode}"
+        ent = torch.from_numpy(g[f"{k}/ent"]).requires_grad_()
+        rel = torch.from_numpy(g[f"{k}/rel"]).requires_grad_()
+        s, n, w = (torch.from_numpy(g[f"{k}/{x}"]) for x in ("sample", "neg", "weight"))
+        gamma = float(g[f"{k}/gamma"])
+        rng_ = ko.embedding_range(gamma, D)
+        pos = tp.forward(model, ent, rel, s, gamma=gamma, embedding_range=rng_)
+        ngs = tp.forward(model, ent, rel, s, n, mode, gamma=gamma, embedding_range=rng_)
+        loss = tp.adversarial(pos, ngs, w, 0.5)
+        loss.backward()
+        np.testing.assert_array_equal(pos.detach().numpy(), g[f"{k}/f32/pos"])
+        np.testing.assert_array_equal(ngs.detach().numpy(), g[f"{k}/f32/neg_score"])
+        np.testing.assert_array_equal(loss.detach().numpy(), g[f"{k}/f32/loss"])
+        np.testing.assert_array_equal(ent.grad.numpy(), g[f"{k}/f32/grad_ent"])
+        np.testing.assert_array_equal(rel.grad.numpy(), g[f"{k}/f32/grad_rel"])
+
+
+def test_torch_port_sampler_matches_reference(sampler_cases):
+    from oracle import torch_port as tp
+    import torch
+
+    g = sampler_cases
+    triples = [tuple(int(x) for x in r) for r in g["triples"]]
+    th, tt = tp.true_sets(triples)
+    rng = np.random.RandomState(42)
+    for step in range(6):
+        out = tp.generate_negatives(rng, torch.from_numpy(g[f"gen{step}/sample"]), str(g[f"gen{step}/mode"]),
+                                    th, tt, int(g["N"]), 16)
+        np.testing.assert_array_equal(out.numpy(), g[f"gen{step}/neg"])
+
+
 def test_negative_sampling_doctest(doctest_pins):
     """mkb/sampling/negative_sampling.py:101-126: sampler indices and RotatE scores, both modes."""
     g = doctest_pins
