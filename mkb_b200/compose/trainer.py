@@ -15,6 +15,7 @@ from __future__ import annotations
 import torch
 
 from .. import ops
+from . import parallel
 
 __all__ = ["DeviceTrainer"]
 
@@ -74,7 +75,7 @@ class DeviceTrainer:
         if h:
             h[1].record()
         if self.distributed:
-            torch.distributed.all_reduce(self.stats[:3], group=self.group)
+            parallel.allreduce_loss_sums(self.stats, self.group)
         if h:
             h[2].record()
         ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
@@ -82,7 +83,7 @@ class DeviceTrainer:
         if h:
             h[3].record()
         if self.distributed:
-            torch.distributed.all_reduce(self._gflat, group=self.group)
+            parallel.allreduce_gradients(self._gflat, self.group)
         self.t += 1
         b1, b2 = self.betas
         ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
@@ -91,5 +92,4 @@ class DeviceTrainer:
 
     def loss(self):
         """Global loss of the last step (host float; synchronises)."""
-        s = self.stats
-        return float((-(s[0] + s[1]) / (2 * s[2])).item())
+        return float(parallel.loss_from_sums(self.stats).item())

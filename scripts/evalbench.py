@@ -1,0 +1,40 @@
+"""Time the filtered all-entity ranking kernel (K5) at BASELINE config 5 shapes (development aid)."""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from mkb_b200 import evaluation, models, ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="RotatE,TransE,ComplEx,DistMult")
+ap.add_argument("--N", type=int, default=40943)
+ap.add_argument("--D", type=int, default=1000)
+ap.add_argument("--Q", type=int, default=3134)
+args = ap.parse_args()
+dev = torch.device("cuda:0")
+N, R, D, Q = args.N, 11, args.D, args.Q
+rng = np.random.RandomState(0)
+tri = np.unique(np.stack([rng.randint(N, size=93003), rng.randint(R, size=93003), rng.randint(N, size=93003)], 1), axis=0)
+test = tri[rng.choice(len(tri), Q, replace=False)]
+for name in args.model.split(","):
+    torch.manual_seed(0)
+    m = getattr(models, name)(hidden_dim=D, entities={i: i for i in range(N)}, relations={i: i for i in range(R)}, gamma=6.0).to(dev)
+    ev = evaluation.Evaluation(entities={i: i for i in range(N)}, relations={i: i for i in range(R)}, batch_size=64,
+                               true_triples=tri)
+    q = torch.from_numpy(test).to(dev)
+    for mode in ("head-batch", "tail-batch"):
+        csr = ev._filter("head" if mode == "head-batch" else "tail", dev)
+        ops.rank_all(m.spec, m.entity_embedding, m.relation_embedding, q[:64], mode, csr)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ranks = ops.rank_all(m.spec, m.entity_embedding, m.relation_embedding, q, mode, csr)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        pairs = Q * N * D
+        print(f"{name} {mode}: {ms:.1f} ms for {Q} queries x {N} entities x D={D} -> {Q/ms*1e3:.0f} rankings/s, "
+              f"{pairs/ms/1e6:.0f} G pair-dims/s, mean rank {ranks.float().mean().item():.1f}", flush=True)
+    t0 = time.time()
+    out = ev.eval(m, [tuple(map(int, r)) for r in test[:512]])
+    print(f"   Evaluation.eval on 512 triples (1024 rankings): {time.time()-t0:.2f} s wall -> {out}", flush=True)

@@ -1,0 +1,72 @@
+"""2-GPU NCCL parity: the batch-parallel step (per-rank fused forward, all-reduce of the loss sums,
+per-rank fused backward, gradient all-reduce) equals one GPU running the global batch.
+Skipped unless two CUDA devices are visible (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from mkb_b200 import models, ops, sampling
+    from mkb_b200.compose import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    Nn, R, D, B, K = 2000, 11, 128, 64, 32
+    rng = np.random.RandomState(0)
+    tri = np.unique(np.stack([rng.randint(Nn, size=20000), rng.randint(R, size=20000), rng.randint(Nn, size=20000)], 1), axis=0)
+    torch.manual_seed(1)
+    m = models.RotatE(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)}, gamma=9.0).to(dev)
+    ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=range(Nn), relations=range(R), seed=5 + rank)
+    order = np.random.RandomState(2).permutation(len(tri))[: B * world]
+    mine = parallel.rank_slices(order, B, world, rank)[0]
+    s = torch.from_numpy(tri[mine]).to(dev)
+    w = torch.from_numpy(np.random.RandomState(3).uniform(0.1, 0.5, len(tri)).astype(np.float32)[mine]).to(dev)
+    neg = ns.generate(s, "head-batch", check=True)
+    ent, rel = m.entity_embedding.detach(), m.relation_embedding.detach()
+    cp, cn = torch.empty(B, device=dev), torch.empty(B, K, device=dev)
+    stats, ws = torch.zeros(4, device=dev), torch.zeros(1 << 16, dtype=torch.uint8, device=dev)
+    flat = torch.zeros(ent.numel() + rel.numel(), device=dev)
+    ge, gr = flat[: ent.numel()].view_as(ent), flat[ent.numel():].view_as(rel)
+    ops.fused_forward_raw(m.spec, ent, rel, s, neg, w, "head-batch", 0.5, cp, cn, stats, ws)
+    parallel.allreduce_loss_sums(stats)
+    ops.fused_backward_raw(m.spec, ent, rel, s, neg, "head-batch", cp, cn, stats, ge, gr)
+    parallel.allreduce_gradients(flat)
+    gs = [torch.empty_like(s) for _ in range(world)]
+    gn = [torch.empty_like(neg) for _ in range(world)]
+    gw = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(gs, s)
+    dist.all_gather(gn, neg)
+    dist.all_gather(gw, w)
+    if rank == 0:
+        S, Ng, W = torch.cat(gs), torch.cat(gn), torch.cat(gw)
+        loss = ops.fused_adversarial_step(m.spec, m.entity_embedding, m.relation_embedding, S, Ng, W, "head-batch", 0.5)
+        loss.backward()
+        out["loss_err"] = abs(loss.item() - parallel.loss_from_sums(stats).item())
+        out["ent_err"] = (m.entity_embedding.grad - ge).abs().max().item() / m.entity_embedding.grad.abs().max().item()
+        out["rel_err"] = (m.relation_embedding.grad - gr).abs().max().item() / m.relation_embedding.grad.abs().max().item()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_step_matches_single_gpu_global_batch():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out["loss_err"] < 1e-6
+    assert out["ent_err"] < 1e-5 and out["rel_err"] < 1e-5

@@ -1,0 +1,88 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU decomposition in mkb_b200/compose/parallel.py:
+per-rank partial loss sums + all-reduce + per-rank gradients with the GLOBAL normaliser + gradient
+all-reduce reproduce the single-process result on the global batch.  The per-rank arithmetic is the
+oracle's (no GPU here); the collectives and the slicing are the product code."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import kge_oracle as ko
+
+MODEL, N, R, D, B, K, GAMMA = "RotatE", 80, 5, 8, 12, 9, 6.0
+
+
+def _problem():
+    rng = np.random.RandomState(3)
+    ent, rel = ko.init_tables(MODEL, N, R, D, GAMMA, seed=5)
+    ent *= 3
+    sample = np.stack([rng.randint(N, size=2 * B), rng.randint(R, size=2 * B), rng.randint(N, size=2 * B)], 1)
+    neg = rng.randint(N, size=(2 * B, K))
+    w = rng.uniform(0.1, 0.5, size=2 * B)
+    return ent, rel, sample.astype(np.int64), neg.astype(np.int64), w
+
+
+def _worker(rank, world, port, out):
+    from mkb_b200.compose import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ent, rel, sample, neg, w = _problem()
+    mine = parallel.rank_slices(np.arange(2 * B), B, world, rank)[0]
+    s, n, ww = sample[mine], neg[mine], w[mine]
+    pos = ko.score(MODEL, ent, rel, s, gamma=GAMMA)
+    ngs = ko.score(MODEL, ent, rel, s, n, "tail-batch", gamma=GAMMA)
+    a = ko._softmax(ngs * 0.5, axis=1)
+    stats = torch.tensor([(ww * ko._logsigmoid(pos[:, 0])).sum(), (ww * (a * ko._logsigmoid(-ngs)).sum(1)).sum(),
+                          ww.sum(), 0.0], dtype=torch.float64)
+    parallel.allreduce_loss_sums(stats)
+    Wg = stats[2].item()
+    gpos = -(ww / (2 * Wg)) * ko._sigmoid(-pos[:, 0])
+    gneg = (ww / (2 * Wg))[:, None] * a * ko._sigmoid(ngs)
+    ge1, gr1 = ko.score_grads(MODEL, ent, rel, s, None, None, gpos[:, None], gamma=GAMMA)
+    ge2, gr2 = ko.score_grads(MODEL, ent, rel, s, n, "tail-batch", gneg, gamma=GAMMA)
+    flat = torch.from_numpy(np.concatenate([(ge1 + ge2).ravel(), (gr1 + gr2).ravel()]))
+    parallel.allreduce_gradients(flat)
+    if rank == 0:
+        out["loss"] = parallel.loss_from_sums(stats).item()
+        out["flat"] = flat.numpy().copy()
+        out["mine"] = mine
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_decomposition_matches_single_process():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ent, rel, sample, neg, w = _problem()
+    loss, _, _, ge, gr = ko.train_step(MODEL, ent, rel, sample, neg, "tail-batch", w, gamma=GAMMA)
+    assert abs(out["loss"] - loss) < 1e-12
+    np.testing.assert_allclose(out["flat"], np.concatenate([ge.ravel(), gr.ravel()]), rtol=1e-10, atol=1e-15)
+    np.testing.assert_array_equal(out["mine"], np.arange(B))
+
+
+def test_rank_slices_cover_the_order_once():
+    from mkb_b200.compose import parallel
+
+    order = np.random.RandomState(0).permutation(1000)
+    for world in (1, 2, 4, 8):
+        per_rank = [parallel.rank_slices(order, 64, world, r) for r in range(world)]
+        assert len({len(p) for p in per_rank}) == 1
+        seen = np.concatenate([np.concatenate(p) for p in per_rank])
+        assert sorted(seen.tolist()) == list(range(1000))
+        for g in range(len(per_rank[0])):
+            sizes = [len(per_rank[r][g]) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1 and max(sizes) <= 64
