@@ -277,36 +277,39 @@ def run_ours(args):
     final_loss = trainer.loss()
     ns.check_status(dev)
 
-    # ---------------- end-to-end arm through the public API, host batches ----------------
+    # ---------------- end-to-end arm: the public API a user calls, host batches ----------------
+    # compose.Pipeline.learn over a datasets.Dataset that lives in (pinned) HOST memory: every step copies
+    # its sample/weight to the device, runs the step, and reads the loss back to the host.
+    from mkb_b200 import compose, datasets, losses
+
     torch.manual_seed(42)
     model2 = getattr(models, mname)(hidden_dim=D, entities={i: i for i in range(N)},
                                     relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     opt = optim.DenseAdam(filter(lambda p: p.requires_grad, model2.parameters()), lr=5e-5)
+    ents, rels = {i: i for i in range(N)}, {i: i for i in range(R)}
 
-    def e2e_step(i):
-        s = host_samples[i].to(dev, non_blocking=True)
-        w = host_weights[i].to(dev, non_blocking=True)
-        neg = ns.generate(s, modes[i])
-        err = ops.fused_adversarial_step(model2.spec, model2.entity_embedding, model2.relation_embedding, s, neg,
-                                         w, modes[i], 0.5)
-        err.backward()
-        if dist:
-            for p in (model2.entity_embedding, model2.relation_embedding):
-                torch.distributed.all_reduce(p.grad)
-        opt.step()
-        opt.zero_grad()
-        return err.item()  # the reference's per-step loss read-back (pipeline.py:242)
+    def host_dataset(rows):  # an epoch of Dataset = one head-batch + one tail-batch per B triples
+        return datasets.Dataset(train=rows, entities=ents, relations=rels, batch_size=B, shuffle=False,
+                                seed=None, pin_memory=True)
 
-    for i in range(warmup):
-        e2e_step(i)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(steps):
-        e2e_step(warmup + i)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    half = (steps + 1) // 2
+    ds_warm = host_dataset(graph[order[: max(warmup // 2, 2)].reshape(-1)])
+    ds_time = host_dataset(graph[order[warmup: warmup + half].reshape(-1)])
+    e2e_steps = 2 * half
+    pipe = compose.Pipeline(epochs=1, device=dev)
+    sys.stderr, _err = open(os.devnull, "w"), sys.stderr  # tqdm's bar
+    try:
+        pipe.learn(model=model2, dataset=ds_warm, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        pipe.learn(model=model2, dataset=ds_time, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
+        e1.record()
+        barrier()
+    finally:
+        sys.stderr = _err
+    e2e_ms = e0.elapsed_time(e1) * steps / e2e_steps  # normalised to `steps` steps
+    e2e_loss = pipe.metric_loss.get()
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
@@ -354,8 +357,10 @@ def run_ours(args):
                          "frac": fwd_gbs / hbm, "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": fwd_ms},
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps,
-                    "api": "sampling.generate + ops.fused_adversarial_step + backward + optim.DenseAdam + loss.item()"},
+                    "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps,
+                    "api": "compose.Pipeline.learn(models.*, datasets.Dataset(host, pinned), sampling.NegativeSampling, "
+                           "optim.DenseAdam, losses.Adversarial): per step H2D sample+weight, D2H loss sums",
+                    "rolling_loss": e2e_loss},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

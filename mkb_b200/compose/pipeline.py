@@ -19,7 +19,10 @@ import torch
 from .. import ops
 from ..losses import Adversarial
 from ..models.base import BaseModel
+from ..optim import DenseAdam
+from ..sampling import NegativeSampling
 from ..utils import Bar
+from .trainer import DeviceTrainer
 
 __all__ = ["Pipeline"]
 
@@ -61,11 +64,58 @@ class Pipeline:
     def _can_fuse(self, model, loss):
         return self.fused and isinstance(model, BaseModel) and type(loss) is Adversarial
 
+    def _device_trainer(self, model, dataset, sampling, optimizer, loss):
+        """The whole step can stay on the device when every piece is ours: fused-capable (model, loss),
+        this package's sampler and ``optim.DenseAdam`` over the model's parameters (one param group)."""
+        if not (self._can_fuse(model, loss) and isinstance(optimizer, DenseAdam)
+                and isinstance(sampling, NegativeSampling) and len(optimizer.param_groups) == 1
+                and model.entity_embedding.is_cuda):
+            return None
+        params = {id(p) for p in optimizer.param_groups[0]["params"]}
+        if not {id(model.entity_embedding), id(model.relation_embedding)} <= params:
+            return None
+        import torch.distributed as dist
+
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        return DeviceTrainer.from_optimizer(model, sampling, optimizer, alpha=loss.alpha,
+                                            max_batch=int(dataset.batch_size), distributed=multi)
+
+    def _learn_on_device(self, trainer, dataset, epoch):
+        """Device-resident epoch: per batch two async H2D copies (skipped when the dataset already
+        lives on the GPU), five kernel launches, and an async D2H copy of the loss sums into pinned
+        memory that is read one step later (the reference's ``error.item()`` without the stall)."""
+        dev = trainer.dev
+        host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        pending = None
+        bar = Bar(dataset=dataset, update_every=10)
+        for k, data in enumerate(bar):
+            sample = data["sample"].to(dev, non_blocking=True)
+            weight = data["weight"].to(dev, non_blocking=True)
+            stats = trainer.step(sample, weight, data["mode"])
+            host[k & 1].copy_(stats, non_blocking=True)
+            done[k & 1].record()
+            if pending is not None:
+                self._record_loss(pending, host, done, bar, epoch)
+            pending = k & 1
+        if pending is not None:
+            self._record_loss(pending, host, done, bar, epoch)
+        trainer.sync_optimizer_state()
+
+    def _record_loss(self, slot, host, done, bar, epoch):
+        done[slot].synchronize()
+        s = host[slot]
+        self.metric_loss.update(float(-(s[0] + s[1]) / (2 * s[2])))
+        bar.set_description(f"Epoch: {epoch}, loss: {self.metric_loss.get():4f}")
+
     def learn(self, model, dataset, sampling, optimizer, loss, evaluation=None):
         fuse = self._can_fuse(model, loss)
+        trainer = self._device_trainer(model, dataset, sampling, optimizer, loss)
         step = 0
         for epoch in range(self.epochs):
-            bar = Bar(dataset=dataset, update_every=10)
+            if trainer is not None:
+                self._learn_on_device(trainer, dataset, epoch)
+            bar = Bar(dataset=dataset if trainer is None else [], update_every=10)
             for data in bar:
                 sample = data["sample"].to(self.device)
                 mode = data["mode"]

@@ -21,6 +21,30 @@ __all__ = ["DeviceTrainer"]
 
 
 class DeviceTrainer:
+    @classmethod
+    def from_optimizer(cls, model, sampling, optimizer, alpha=0.5, max_batch=1024, **kw):
+        """Adopt the hyper-parameters (and, if any, the moments) of a ``mkb_b200.optim.DenseAdam`` built
+        over ``model.parameters()`` and keep that optimizer's state pointing at the trainer's buffers,
+        so ``optimizer.state_dict()`` stays meaningful after training."""
+        group = optimizer.param_groups[0]
+        t = cls(model, sampling, lr=group["lr"], betas=tuple(group["betas"]), eps=group["eps"], alpha=alpha,
+                max_batch=max_batch, **kw)
+        for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
+            st = optimizer.state[p]
+            if st:
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                t.t = max(t.t, int(st["step"]))
+            st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, t.t
+        t._optimizer = optimizer
+        return t
+
+    def sync_optimizer_state(self):
+        opt = getattr(self, "_optimizer", None)
+        if opt is not None:
+            for p in (self.model.entity_embedding, self.model.relation_embedding):
+                opt.state[p]["step"] = self.t
+
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False):
         ent, rel = model.entity_embedding, model.relation_embedding
@@ -65,7 +89,12 @@ class DeviceTrainer:
         neg = self.neg[:B]
         coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
         s = self.sampling
-        ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg)
+        if s.pool == "reference":  # the reference's host-drawn shared pool: 2K ids cross PCIe
+            pool = torch.from_numpy(s._rng.randint(s.n_entity, size=self.K * 2).astype("int64")).to(
+                self.dev, non_blocking=True)
+            ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg)
+        else:
+            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg)
         s._calls += 1
         h = self.hooks
         if h:

@@ -41,13 +41,14 @@ class Dataset:
     (mkb/datasets/dataset.py:94-186).  Iterating yields, alternately, a head-batch and a tail-batch
     dict ``{"sample": int64[B,3], "weight": float32[B], "mode": str}`` (:188-194).
 
-    Extra keyword (not in the reference): ``device`` — keep triples/weights on that device and yield
-    batches there (no per-step H2D copy).
+    Extra keywords (not in the reference): ``device`` — keep triples/weights on that device and yield
+    batches there (no per-step H2D copy); ``pin_memory`` — host batches are gathered into a small ring of
+    page-locked buffers so the consumer's ``.to(device, non_blocking=True)`` is a true async copy.
     """
 
     def __init__(self, train, batch_size, entities=None, relations=None, valid=None, test=None,
                  shuffle=True, classification=False, pre_compute=True, num_workers=1, seed=42,
-                 classification_valid=None, classification_test=None, device=None):
+                 classification_valid=None, classification_test=None, device=None, pin_memory=False):
         if classification:
             raise NotImplementedError(
                 "classification mode feeds ConvE/BCE, which is outside the KGE hot path this package covers")
@@ -59,6 +60,8 @@ class Dataset:
         self.num_workers = num_workers
         self.seed = seed
         self.device = torch.device(device) if device is not None else None
+        self.pin_memory = bool(pin_memory) and self.device is None and torch.cuda.is_available()
+        self._ring, self._slot = None, 0
 
         if entities is None:  # dataset.py:116-127
             self.entities = self.mapping_entities()
@@ -122,10 +125,21 @@ class Dataset:
 
     def _batches(self, mode, order):
         order = order.to(self._triples.device)
+        if self.pin_memory and self._ring is None:
+            self._ring = [(torch.empty((self.batch_size, 3), dtype=torch.int64).pin_memory(),
+                           torch.empty(self.batch_size, dtype=torch.float32).pin_memory()) for _ in range(8)]
         for lo in range(0, order.shape[0], self.batch_size):
             idx = order[lo:lo + self.batch_size]
-            yield {"sample": self._triples.index_select(0, idx), "weight": self._weights.index_select(0, idx),
-                   "mode": mode}
+            if self.pin_memory:
+                sbuf, wbuf = self._ring[self._slot]
+                self._slot = (self._slot + 1) % len(self._ring)
+                n = idx.shape[0]
+                torch.index_select(self._triples, 0, idx, out=sbuf[:n])
+                torch.index_select(self._weights, 0, idx, out=wbuf[:n])
+                yield {"sample": sbuf[:n], "weight": wbuf[:n], "mode": mode}
+            else:
+                yield {"sample": self._triples.index_select(0, idx), "weight": self._weights.index_select(0, idx),
+                       "mode": mode}
 
     def __iter__(self):
         head = self._batches("head-batch", self._order())

@@ -395,3 +395,47 @@ def test_cpu_tensors_fail_loudly():
     m = models.TransE(hidden_dim=4, entities={0: 0, 1: 1}, relations={0: 0}, gamma=3)
     with pytest.raises(RuntimeError, match="CUDA only"):
         m(torch.tensor([[0, 0, 1]]))
+
+
+# ------------------------------------------------------------------------------------------------
+# Pipeline: the three routes (generic three-call, fused autograd, device-resident) agree
+# ------------------------------------------------------------------------------------------------
+def _toy_pipeline(route, pool, epochs=2):
+    from mkb_b200 import compose, datasets
+
+    rng = np.random.RandomState(4)
+    Nn, R = 120, 4
+    tri = sorted({(int(rng.randint(Nn)), int(rng.randint(R)), int(rng.randint(Nn))) for _ in range(900)})
+    ents, rels = {i: i for i in range(Nn)}, {i: i for i in range(R)}
+    ds = datasets.Dataset(train=tri[:700], valid=tri[700:800], test=tri[800:], entities=ents, relations=rels,
+                          batch_size=64, shuffle=True, seed=42, pin_memory=(route == "device"))
+    torch.manual_seed(7)
+    m = models.RotatE(hidden_dim=16, entities=ents, relations=rels, gamma=6).to(DEV)
+    ns = sampling.NegativeSampling(size=8, train_triples=ds.train, entities=ents, relations=rels, seed=42, pool=pool)
+    params = [p for p in m.parameters() if p.requires_grad]
+    opt = optim.DenseAdam(params, lr=0.01) if route == "device" else torch.optim.Adam(params, lr=0.01)
+    ev = evaluation.Evaluation(entities=ents, relations=rels, batch_size=8, true_triples=ds.true_triples, device=DEV)
+    pipe = compose.Pipeline(epochs=epochs, eval_every=1, device=DEV, fused=(route != "generic"))
+    pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5), evaluation=ev)
+    return m, pipe
+
+
+@pytest.mark.parametrize("pool", ("independent", "reference"))
+def test_pipeline_routes_agree(pool, capsys):
+    ref, p0 = _toy_pipeline("generic", pool)
+    for route in ("fused", "device"):
+        m, p = _toy_pipeline(route, pool)
+        torch.testing.assert_close(m.entity_embedding, ref.entity_embedding, rtol=2e-3, atol=2e-4)
+        torch.testing.assert_close(m.relation_embedding, ref.relation_embedding, rtol=2e-3, atol=2e-4)
+        assert abs(p.metric_loss.get() - p0.metric_loss.get()) < 1e-4
+        assert set(p.valid_scores) == {"MRR", "MR", "HITS@1", "HITS@3", "HITS@10", "MRR_relations", "MR_relations",
+                                       "HITS@1_relations", "HITS@3_relations", "HITS@10_relations"}
+        assert abs(p.test_scores["MR"] - p0.test_scores["MR"]) <= 1.0
+    out = capsys.readouterr().out
+    assert "Validation:" in out and "HITS@10" in out
+
+
+def test_training_reduces_loss_and_improves_ranks():
+    m, pipe = _toy_pipeline("device", "independent", epochs=30)
+    assert pipe.metric_loss.get() < 0.55
+    assert pipe.valid_scores["MR"] < 55  # random ranking over 120 entities sits near 60
