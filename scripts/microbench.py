@@ -37,6 +37,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="cfg2,cfg3,cfg1,cfg4,cfg2t")
     ap.add_argument("--pooled", action="store_true")
+    ap.add_argument("--band", type=int, default=0, help="restrict negative ids to [0, band)")
+    ap.add_argument("--sorted", action="store_true", help="sort each row of negatives by id")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -52,7 +54,10 @@ def main():
             pool = torch.randint(N, (2 * K,), generator=g)
             n = pool[:K].repeat(B, 1).to(dev)
         else:
-            n = torch.randint(N, (B, K), generator=g).to(dev)
+            n = torch.randint(args.band or N, (B, K), generator=g)
+            if args.sorted:
+                n = n.sort(dim=1).values
+            n = n.to(dev)
         w = (torch.rand(B, generator=g) * 0.4 + 0.1).to(dev)
         ent, rel = m.entity_embedding.detach(), m.relation_embedding.detach()
         coef_pos = torch.empty(B, device=dev); coef_neg = torch.empty(B, K, device=dev)

@@ -436,6 +436,15 @@ def test_pipeline_routes_agree(pool, capsys):
 
 
 def test_training_reduces_loss_and_improves_ranks():
-    m, pipe = _toy_pipeline("device", "independent", epochs=30)
-    assert pipe.metric_loss.get() < 0.55
-    assert pipe.valid_scores["MR"] < 55  # random ranking over 120 entities sits near 60
+    """The toy graph is random (nothing to generalise), so check memorisation: the loss falls and the
+    filtered rank of TRAINING triples beats the random-ranking mean of ~60 by a wide margin."""
+    m0, p0 = _toy_pipeline("device", "independent", epochs=1)
+    m, pipe = _toy_pipeline("device", "independent", epochs=40)
+    assert pipe.metric_loss.get() < p0.metric_loss.get() - 0.1
+    rng = np.random.RandomState(4)
+    tri = sorted({(int(rng.randint(120)), int(rng.randint(4)), int(rng.randint(120))) for _ in range(900)})
+    ev = evaluation.Evaluation(entities={i: i for i in range(120)}, relations={i: i for i in range(4)}, batch_size=8,
+                               true_triples=tri)
+    before = ev.eval(m0, tri[:200])["MR"]
+    after = ev.eval(m, tri[:200])["MR"]
+    assert after < 0.6 * before, (before, after)
