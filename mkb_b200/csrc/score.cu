@@ -17,6 +17,8 @@
 // Reference being replaced: mkb/models/base.py:132-207 (gathers), transe.py:65-76,
 // distmult.py:63-75, complex.py:65-85, rotate.py:69-99 (scores), losses/adversarial.py:21-30,
 // and autograd's backward of all of them (compose/pipeline.py:236).
+#include <cstdlib>
+
 #include "kge_common.cuh"
 
 namespace kge {
@@ -114,7 +116,7 @@ __device__ __forceinline__ float row_reduce(const float* __restrict__ row, const
 // forward with candidates: grid = (B, K-slices); FUSED => K-slices == 1 and the loss is folded in
 // ------------------------------------------------------------------------------------------------
 template <int M, bool HEAD, int VEC, bool FUSED>
-__global__ void __launch_bounds__(kThreads) score_neg_kernel(FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 4) score_neg_kernel(FwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[33];
@@ -519,6 +521,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
     const int want = (4 * sm_count() + (int)B - 1) / (int)B;
     const int maxks = (p.K + 63) / 64;
     ks = want < 1 ? 1 : (want > maxks ? maxks : want);
+    if (const char* e = getenv("KGE_KS")) ks = atoi(e) > 0 ? atoi(e) : ks;
   }
   p.k_per_cta = p.K > 0 ? (p.K + ks - 1) / ks : 0;
   if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
@@ -582,6 +585,7 @@ extern "C" int kge_score_fwd(const kge_tables_t* t, int mode, const int64_t* sam
   const int want = (4 * sm_count() + (int)B - 1) / (int)B;
   const int maxks = (p.K + 63) / 64;
   int ks = want < 1 ? 1 : (want > maxks ? maxks : want);
+  if (const char* e = getenv("KGE_KS")) ks = atoi(e) > 0 ? atoi(e) : ks;
   p.k_per_cta = (p.K + ks - 1) / ks;
   ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
   const size_t smem = (size_t)entity_comps(t->model) * p.Dp * sizeof(float);
