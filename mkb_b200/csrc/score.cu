@@ -236,7 +236,7 @@ struct BwdParams {
 constexpr int kTileK = 256;
 
 template <int M, bool HEAD, int VEC>
-__global__ void __launch_bounds__(kThreads) score_bwd_kernel(BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC]
   __shared__ int64_t s_idx[kTileK];
@@ -261,18 +261,21 @@ __global__ void __launch_bounds__(kThreads) score_bwd_kernel(BwdParams p) {
   for (int cb = 0; cb * tpg * VEC < p.D; ++cb) {
     const int d = (cb * tpg + lt) * VEC;
     const bool active = d < p.D;
-    float a0[VEC] = {}, a1[VEC] = {}, r0[VEC] = {}, r1[VEC] = {}, q0[VEC] = {}, q1[VEC] = {};
+    // q is the only per-element state carried through the K loop; the fixed row and the relation
+    // are re-read afterwards for the chain rule (L1/L2 hits) instead of pinning 16 registers.
+    float q0[VEC] = {}, q1[VEC] = {};
     float dq0[VEC] = {}, dq1[VEC] = {};
     if (active) {
-      float rr0[VEC], rr1[VEC] = {};
+      float a0[VEC], a1[VEC] = {}, rr0[VEC], rr1[VEC] = {};
       ld_global<VEC>(fixed + d, a0);
       if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
       ld_global<VEC>(relrow + d, rr0);
       if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
-        make_query<M, HEAD>(a0[v], a1[v], r0[v], r1[v], q0[v], q1[v]);
+        float r0, r1;
+        rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0, r1);
+        make_query<M, HEAD>(a0[v], a1[v], r0, r1, q0[v], q1[v]);
       }
     }
     // ---- candidates: group g takes every G-th row of the tile
@@ -341,6 +344,16 @@ __global__ void __launch_bounds__(kThreads) score_bwd_kernel(BwdParams p) {
     }
     // ---- positive term + chain rule to the positive's own rows (group 0 only)
     if (grp == 0 && active) {
+      float a0[VEC], a1[VEC] = {}, r0[VEC], r1[VEC];
+      {
+        float rr0[VEC], rr1[VEC] = {};
+        ld_global<VEC>(fixed + d, a0);
+        if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
+        ld_global<VEC>(relrow + d, rr0);
+        if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
+      }
       float gt0[VEC] = {}, gt1[VEC] = {};  // -> tail row
       float gh0[VEC] = {}, gh1[VEC] = {};  // -> head row
       float gr0[VEC] = {}, gr1[VEC] = {};  // -> relation row (stored form)
