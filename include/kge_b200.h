@@ -131,8 +131,10 @@ int kge_fused_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, i
  *        head-batch: key (r,t) -> sorted true heads;   tail-batch: key (h,r) -> sorted true tails.
  * kge_sample_negatives: independent Philox4x32-10 stream per output slot (seed, offset given per
  *     call; the caller advances offset by 1 per call).  Rejected candidates (members of the true
- *     set) are redrawn.  status (device int32, OR-ed): bit0 = key not found (the reference raises
- *     KeyError), bit1 = a true set covers every entity.
+ *     set) are redrawn.  sort_rows != 0 (and K <= 2048) returns every row sorted ascending by id:
+ *     the same multiset of negatives (the loss does not depend on their order) in the order that
+ *     keeps the scoring kernels' gathers L2-friendly.  status (device int32, OR-ed): bit0 = key not
+ *     found (the reference raises KeyError), bit1 = a true set covers every entity.
  * kge_filter_pool: the reference's exact semantics given the batch's host-drawn pool
  *     (RandomState.randint(n_entity, 2*size), :166): each positive takes the first K survivors of
  *     the shared pool, repeating cyclically when fewer survive (:176-195).  bit2 of status = no
@@ -146,7 +148,7 @@ typedef struct kge_filter_csr {
 } kge_filter_csr_t;
 
 int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
-                         int64_t K, int64_t n_entity, uint64_t seed, uint64_t offset,
+                         int64_t K, int64_t n_entity, uint64_t seed, uint64_t offset, int sort_rows,
                          int64_t* negatives, int32_t* status, kge_stream_t stream);
 int kge_filter_pool(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
                     int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,

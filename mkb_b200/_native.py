@@ -58,7 +58,7 @@ PROTOTYPES = {
     "kge_fused_bwd": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, _P, _P, _P,
                                 _P, _P, _P]),
     "kge_sample_negatives": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64,
-                                       C.c_uint64, C.c_uint64, _P, _P, _P]),
+                                       C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]),
     "kge_filter_pool": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,
                                   _P, _P, _P]),
     "kge_rank_workspace_bytes": (C.c_size_t, [C.POINTER(KgeTables), _I64]),

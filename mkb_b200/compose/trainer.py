@@ -94,7 +94,8 @@ class DeviceTrainer:
                 self.dev, non_blocking=True)
             ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg)
         else:
-            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg)
+            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg,
+                                 sort_rows=s.sort_rows)
         s._calls += 1
         h = self.hooks
         if h:

@@ -68,12 +68,16 @@ __device__ __forceinline__ void positive_segment(const kge_filter_csr_t& f, bool
   }
 }
 
+constexpr int kMaxSortK = 2048;  // rows up to this length are sorted in shared memory
+
 __global__ void __launch_bounds__(kThreads) sample_negatives_kernel(kge_filter_csr_t f, int head_mode,
                                                                     const int64_t* __restrict__ sample,
                                                                     int64_t K, int64_t n_entity,
                                                                     uint64_t seed, uint64_t offset,
+                                                                    int sort_pow2,
                                                                     int64_t* __restrict__ out,
                                                                     int32_t* status) {
+  extern __shared__ uint32_t s_ids[];  // sort_pow2 entries when sorting
   __shared__ int64_t s_seg[2];
   const int64_t i = blockIdx.x;
   if (threadIdx.x == 0) positive_segment(f, head_mode != 0, sample, i, n_entity, s_seg[0], s_seg[1], status);
@@ -105,7 +109,31 @@ __global__ void __launch_bounds__(kThreads) sample_negatives_kernel(kge_filter_c
       }
       if (!found) atomicOr(status, 2);
     }
-    out[i * K + j] = cand;
+    if (sort_pow2) s_ids[j] = (uint32_t)cand;
+    else out[i * K + j] = cand;
+  }
+  if (sort_pow2) {
+    // Ascending bitonic sort of the row: the set of negatives is unchanged (the loss is a symmetric
+    // function of the row), but every CTA of the scoring kernels then walks the entity table in the
+    // same direction, which keeps the active band of the table (and of its gradient) L2-resident.
+    for (int j = (int)K + threadIdx.x; j < sort_pow2; j += blockDim.x) s_ids[j] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int size = 2; size <= sort_pow2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = threadIdx.x; t < (sort_pow2 >> 1); t += blockDim.x) {
+          const int lo_i = 2 * t - (t & (stride - 1));
+          const int hi_i = lo_i + stride;
+          const bool up = (lo_i & size) == 0;
+          const uint32_t a = s_ids[lo_i], b = s_ids[hi_i];
+          if ((a > b) == up) {
+            s_ids[lo_i] = b;
+            s_ids[hi_i] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int64_t j = threadIdx.x; j < K; j += blockDim.x) out[i * K + j] = (int64_t)s_ids[j];
   }
 }
 
@@ -158,7 +186,7 @@ static int check_filter(const kge_filter_csr_t* f) {
 
 extern "C" int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, const int64_t* sample,
                                     int64_t B, int64_t K, int64_t n_entity, uint64_t seed,
-                                    uint64_t offset, int64_t* negatives, int32_t* status,
+                                    uint64_t offset, int sort_rows, int64_t* negatives, int32_t* status,
                                     kge_stream_t stream) {
   int rc = check_filter(filter);
   if (rc) return rc;
@@ -167,8 +195,13 @@ extern "C" int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, co
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   if (B == 0) return KGE_OK;
   const int threads = K >= 256 ? 256 : (int)((K + 31) / 32 * 32);
-  sample_negatives_kernel<<<(unsigned)B, threads, 0, (cudaStream_t)stream>>>(
-      *filter, mode == KGE_HEAD_BATCH, sample, K, n_entity, seed, offset, negatives, status);
+  int pow2 = 0;
+  if (sort_rows && K > 1 && K <= kMaxSortK) {
+    pow2 = 2;
+    while (pow2 < K) pow2 <<= 1;
+  }
+  sample_negatives_kernel<<<(unsigned)B, threads, (size_t)pow2 * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      *filter, mode == KGE_HEAD_BATCH, sample, K, n_entity, seed, offset, pow2, negatives, status);
   KGE_LAUNCH_CHECK();
   return KGE_OK;
 }

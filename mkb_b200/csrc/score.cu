@@ -529,10 +529,16 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.tpg = tpg;
   const int G = kThreads / tpg;
   // K-slices: enough CTAs to fill the machine when B alone is small
+  // K-slices (gridDim.y; CTAs are issued x-fastest, i.e. slice-major): (a) enough CTAs to fill the
+  // machine when B is small, (b) with id-sorted rows slice s of every positive covers the same band
+  // of the entity table, so table + gradient of the active band stay L2-resident (~64 MB budget).
   int ks = 1;
   if (p.K > 0) {
-    const int want = (4 * sm_count() + (int)B - 1) / (int)B;
-    const int maxks = (p.K + 63) / 64;
+    const int fill = (4 * sm_count() + (int)B - 1) / (int)B;
+    const double tbl = 2.0 * (double)t->n_entity * p.ent_stride * sizeof(float);
+    const int band = (int)(tbl / (64.0 * 1024 * 1024)) + 1;
+    const int want = fill > band ? fill : band;
+    const int maxks = (p.K + 31) / 32;
     ks = want < 1 ? 1 : (want > maxks ? maxks : want);
     if (const char* e = getenv("KGE_KS")) ks = atoi(e) > 0 ? atoi(e) : ks;
   }

@@ -285,7 +285,7 @@ class FilterCSR:
                               self.keys.shape[0])
 
 
-def sample_negatives(csr, sample, mode, size, n_entity, seed, offset, status=None, out=None):
+def sample_negatives(csr, sample, mode, size, n_entity, seed, offset, status=None, out=None, sort_rows=True):
     lib = N.load()
     N.require_cuda(sample, csr.keys)
     B = sample.shape[0]
@@ -297,7 +297,7 @@ def sample_negatives(csr, sample, mode, size, n_entity, seed, offset, status=Non
     fs = csr.struct()
     with torch.cuda.device(dev):
         N.check(lib.kge_sample_negatives(C.byref(fs), _mode_id(mode), N.ptr(sample), B, size, n_entity,
-                                         C.c_uint64(seed & (2**64 - 1)), C.c_uint64(offset), N.ptr(out),
+                                         C.c_uint64(seed & (2**64 - 1)), C.c_uint64(offset), int(bool(sort_rows)), N.ptr(out),
                                          N.ptr(status), N.stream_ptr(dev)), "kge_sample_negatives")
     N.count_launch()
     return out, status

@@ -28,14 +28,16 @@ class NegativeSampling:
     forms a training triple with the positive (negative_sampling.py:133-201).
 
     pool="independent" (default): every output slot draws independently from its own Philox4x32-10
-        stream on the GPU — no host work, no H2D copy on the step.
+        stream on the GPU — no host work, no H2D copy on the step.  Rows come back sorted by id
+        (``sort_rows=True``): same multiset, order chosen for the scoring kernels' cache behaviour.
     pool="reference": the reference's exact semantics — ONE pool of ``2*size`` candidates per call
         drawn from ``np.random.RandomState(seed).randint`` (:151,:166), every positive takes the first
         ``size`` survivors of that shared pool (cyclically repeated when fewer survive, :176-195).
         The 2*size ids are the only bytes copied to the device.
     """
 
-    def __init__(self, size, train_triples, entities, relations, seed=42, pool="independent", device=None):
+    def __init__(self, size, train_triples, entities, relations, seed=42, pool="independent", device=None,
+                 sort_rows=True):
         if pool not in ("independent", "reference"):
             raise ValueError("pool must be 'independent' or 'reference'")
         self.size = size
@@ -43,6 +45,7 @@ class NegativeSampling:
         self.n_relation = len(relations)
         self.seed = seed
         self.pool = pool
+        self.sort_rows = sort_rows  # independent pool only: rows ascending by id (L2-friendly gathers)
         self._rng = np.random.RandomState(seed)
         self._calls = 0
         self._host_csr = {side: build_filter_csr(train_triples, self.n_entity, side) for side in ("head", "tail")}
@@ -102,7 +105,8 @@ class NegativeSampling:
             pool = torch.from_numpy(self._rng.randint(self.n_entity, size=self.size * 2).astype(np.int64))
             out, _ = ops.filter_pool(csr, sample, mode, self.size, self.n_entity, pool.to(device), status)
         else:
-            out, _ = ops.sample_negatives(csr, sample, mode, self.size, self.n_entity, self.seed, self._calls, status)
+            out, _ = ops.sample_negatives(csr, sample, mode, self.size, self.n_entity, self.seed, self._calls, status,
+                                          sort_rows=self.sort_rows)
         self._calls += 1
         if check:
             self.check_status(device)

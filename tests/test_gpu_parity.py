@@ -448,3 +448,15 @@ def test_training_reduces_loss_and_improves_ranks():
     before = ev.eval(m0, tri[:200])["MR"]
     after = ev.eval(m, tri[:200])["MR"]
     assert after < 0.6 * before, (before, after)
+
+
+def test_sorted_rows_are_the_same_multiset(sampler_cases):
+    g = sampler_cases
+    triples, Nn, _ = _sampler(g, "independent")
+    a = sampling.NegativeSampling(size=40, train_triples=triples, entities=range(Nn), relations=range(4), seed=9)
+    b = sampling.NegativeSampling(size=40, train_triples=triples, entities=range(Nn), relations=range(4), seed=9,
+                                  sort_rows=False)
+    s = _t(g["gen1/sample"])
+    xa, xb = a.generate(s, "tail-batch").cpu().numpy(), b.generate(s, "tail-batch").cpu().numpy()
+    np.testing.assert_array_equal(xa, np.sort(xb, axis=1))
+    assert (np.diff(xa, axis=1) >= 0).all() and not (np.diff(xb, axis=1) >= 0).all()
