@@ -300,18 +300,25 @@ def run_ours(args):
     sys.stderr, _err = open(os.devnull, "w"), sys.stderr  # tqdm's bar
     try:
         pipe.learn(model=model2, dataset=ds_warm, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        pipe.learn(model=model2, dataset=ds_time, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
-        e1.record()
-        barrier()
+        e2e_passes = []
+        for _ in range(2):  # two full passes; the faster one is reported (a cold first pass has been seen
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)  # to pay
+            barrier()  # one-off driver/allocator costs), both are listed in e2e.passes_ms_per_step
+            e0.record()
+            pipe.learn(model=model2, dataset=ds_time, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
+            e1.record()
+            barrier()
+            e2e_passes.append(e0.elapsed_time(e1) / e2e_steps)
     finally:
         sys.stderr = _err
-    e2e_ms = e0.elapsed_time(e1) * steps / e2e_steps  # normalised to `steps` steps
+    e2e_ms = min(e2e_passes) * steps  # per-step time of the faster pass x `steps`
     e2e_loss = pipe.metric_loss.get()
 
     # ---------------- reduce over ranks ----------------
+    e2e_passes_t = torch.tensor(e2e_passes, dtype=torch.float64, device=dev)
+    if dist:
+        torch.distributed.all_reduce(e2e_passes_t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(e2e_passes_t.min().item()) * steps
     t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
     if dist:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -360,7 +367,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps,
                     "api": "compose.Pipeline.learn(models.*, datasets.Dataset(host, pinned), sampling.NegativeSampling, "
                            "optim.DenseAdam, losses.Adversarial): per step H2D sample+weight, D2H loss sums",
-                    "rolling_loss": e2e_loss},
+                    "rolling_loss": e2e_loss, "passes_ms_per_step": e2e_passes_t.tolist(),
+                    "note": "faster of two timed passes of Pipeline.learn over the same K-step dataset"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

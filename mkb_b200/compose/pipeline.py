@@ -77,8 +77,12 @@ class Pipeline:
         import torch.distributed as dist
 
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        return DeviceTrainer.from_optimizer(model, sampling, optimizer, alpha=loss.alpha,
-                                            max_batch=int(dataset.batch_size), distributed=multi)
+        key = (id(model), id(sampling), id(optimizer), float(loss.alpha), int(dataset.batch_size), multi)
+        if getattr(self, "_trainer_key", None) != key:  # keep buffers across learn() calls
+            self._trainer = DeviceTrainer.from_optimizer(model, sampling, optimizer, alpha=loss.alpha,
+                                                         max_batch=int(dataset.batch_size), distributed=multi)
+            self._trainer_key = key
+        return self._trainer
 
     def _learn_on_device(self, trainer, dataset, epoch):
         """Device-resident epoch: per batch two async H2D copies (skipped when the dataset already
