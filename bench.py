@@ -232,7 +232,7 @@ def run_ours(args):
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev)
-    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist)
+    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, chunks=args.chunks)
 
     # this rank's batches: disjoint slices of a seeded permutation of the training triples
     from mkb_b200.datasets.dataset import subsampling_weights
@@ -353,7 +353,8 @@ def run_ours(args):
                 "parallelism": f"dp{world}: replicated tables, all-reduce of 3 loss sums + dense grads" if dist else "single GPU",
                 "l2": "working set per step (tables+grads+Adam moments = "
                       f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
-                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)",
+                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)" if not trainer.chunks
+                        else f"sample_negatives + fused_fwd + {len(trainer.chunks)} x [fused_bwd_chunk | all-reduce + adam chunk on a side stream]",
                 "final_loss": final_loss,
             },
             "roofline": {
@@ -390,6 +391,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=None,
+                    help="column chunks of the pipelined backward/all-reduce/Adam (default: 1 on one GPU, 4 on several)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

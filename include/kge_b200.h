@@ -124,6 +124,18 @@ int kge_fused_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, i
                   const float* stats, const float* grad_loss, float* grad_entity,
                   float* grad_relation, kge_stream_t stream);
 
+/* K3, one column chunk: the same backward restricted to hidden-dim columns [col0, col0 + ncols)
+ * (of both components).  The backward is element-wise in the hidden dim, so the chunks of one step
+ * are independent launches; grad_entity_chunk / grad_relation_chunk are dense
+ * [n_entity, NC*ncols] / [n_relation, RC*ncols] buffers for that chunk only, which makes each chunk's
+ * gradient one contiguous region: the multi-GPU step all-reduces chunk c (and runs its Adam update,
+ * kge_adam_step_chunk) while chunk c+1 is still being computed.  col0 and ncols must be multiples
+ * of 4 for the vector path. */
+int kge_fused_bwd_chunk(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                        const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
+                        const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,
+                        float* grad_entity_chunk, float* grad_relation_chunk, kge_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4  negative sampling on the device.  Replaces NegativeSampling.generate
  *     (mkb/sampling/negative_sampling.py:158-201) and the dictionaries of positive_triples (:7-28),
@@ -176,6 +188,13 @@ int kge_rank_all(const kge_tables_t* tables, int mode, const int64_t* queries, i
 int kge_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
                   kge_stream_t stream);
+
+/* Adam on one column chunk: grad_chunk is dense [rows, comps*ncols]; param and the moments keep the
+ * table layout (row stride row_stride floats, second component at +im_off, chunk at column col0). */
+int kge_adam_step_chunk(float* param, float* grad_chunk, float* exp_avg, float* exp_avg_sq, int64_t rows,
+                        int32_t comps, int32_t ncols, int32_t col0, int32_t row_stride, int32_t im_off,
+                        int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
+                        kge_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ class DeviceTrainer:
                 opt.state[p]["step"] = self.t
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
-                 process_group=None, distributed=False):
+                 process_group=None, distributed=False, chunks=None):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -59,10 +59,35 @@ class DeviceTrainer:
         self.group = process_group
         K = sampling.size
         f32 = dict(dtype=torch.float32, device=self.dev)
-        # one flat buffer for both gradients => a single all-reduce in the multi-GPU path
+        # Gradient storage.  chunks == 1: one flat buffer in the tables' layout.  chunks > 1: the hidden
+        # dim is cut into column chunks and the buffer is chunk-major ([entity chunk c | relation chunk c]
+        # contiguous), so the backward of chunk c, its all-reduce and its Adam update form a pipeline:
+        # while the main stream computes chunk c+1, a side stream reduces and applies chunk c.
+        D = model.hidden_dim
+        self.nc = self.ent.shape[1] // D
+        self.rc = self.rel.shape[1] // D
+        if chunks is None:
+            chunks = 4 if distributed else 1
+        if D % 4 != 0 or D < 128 * chunks:
+            chunks = 1
+        self.chunks = []
         self._gflat = torch.zeros(self.ent.numel() + self.rel.numel(), **f32)
-        self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
-        self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
+        if chunks == 1:
+            self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
+            self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
+        else:
+            width = -(-D // chunks // 32) * 32
+            off, col = 0, 0
+            while col < D:
+                w = min(width, D - col)
+                ne, nr = self.ent.shape[0] * self.nc * w, self.rel.shape[0] * self.rc * w
+                flat = self._gflat[off: off + ne + nr]
+                self.chunks.append((col, w, flat, flat[:ne].view(self.ent.shape[0], self.nc * w),
+                                    flat[ne:].view(self.rel.shape[0], self.rc * w)))
+                off += ne + nr
+                col += w
+            self.side = torch.cuda.Stream(device=self.dev)
+            self._chunk_done = [torch.cuda.Event() for _ in self.chunks]
         self.m_ent, self.v_ent = torch.zeros_like(self.ent), torch.zeros_like(self.ent)
         self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
         self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
@@ -78,7 +103,6 @@ class DeviceTrainer:
                      for m in ("head-batch", "tail-batch")}
         self.hooks = None  # optional (pre_fwd, post_fwd, pre_bwd, post_bwd) event recorders for bench.py
 
-    launches_per_step = 5
 
     def step(self, sample, weight, mode):
         """One optimisation step on a device-resident batch; returns the device loss scalar (a view
@@ -108,16 +132,37 @@ class DeviceTrainer:
             parallel.allreduce_loss_sums(self.stats, self.group)
         if h:
             h[2].record()
-        ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
-                               self.g_ent, self.g_rel)
-        if h:
-            h[3].record()
-        if self.distributed:
-            parallel.allreduce_gradients(self._gflat, self.group)
         self.t += 1
         b1, b2 = self.betas
-        ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
-        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        if not self.chunks:
+            ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg,
+                                   self.stats, self.g_ent, self.g_rel)
+            if h:
+                h[3].record()
+            if self.distributed:
+                parallel.allreduce_gradients(self._gflat, self.group)
+            ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps,
+                          zero_grad=True)
+            ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps,
+                          zero_grad=True)
+            return self.stats
+        main = torch.cuda.current_stream(self.dev)
+        D = self.model.hidden_dim
+        for c, (col, w, flat, ge, gr) in enumerate(self.chunks):
+            ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg,
+                                         self.stats, col, w, ge, gr)
+            self._chunk_done[c].record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self._chunk_done[c])
+                if self.distributed:
+                    parallel.allreduce_gradients(flat, self.group)
+                ops.adam_step_chunk(self.ent, ge, self.m_ent, self.v_ent, self.nc, w, col, D, self.t, self.lr,
+                                    b1, b2, self.eps)
+                ops.adam_step_chunk(self.rel, gr, self.m_rel, self.v_rel, self.rc, w, col, D, self.t, self.lr,
+                                    b1, b2, self.eps)
+        if h:
+            h[3].record()
+        main.wait_stream(self.side)
         return self.stats
 
     def loss(self):

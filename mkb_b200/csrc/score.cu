@@ -226,8 +226,12 @@ struct BwdParams {
   const float* grad_loss;
   float* grad_ent;
   float* grad_rel;
-  int B, K, D;
+  int B, K, D;  // D = number of hidden-dim columns this launch covers (a column chunk)
+  int col0;     // first column of the chunk in the tables
+  int im_off;   // offset of the im / second component inside a table row (= hidden_dim)
   int ent_stride, rel_stride;
+  int g_im_off;  // same three for the gradient buffers, which may be chunk-major (dense per chunk)
+  int g_ent_stride, g_rel_stride;
   int k_per_cta;
   int tpg;  // threads per group (multiple of 32, divides 256)
   float phase_div;
@@ -247,10 +251,10 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   const int grp = tid / tpg, lt = tid - grp * tpg;
   const int64_t i = blockIdx.x;
   const int64_t hid = p.sample[3 * i + 0], rid = p.sample[3 * i + 1], tidx = p.sample[3 * i + 2];
-  const float* hrow = p.ent + hid * (int64_t)p.ent_stride;
-  const float* trow = p.ent + tidx * (int64_t)p.ent_stride;
+  const float* hrow = p.ent + hid * (int64_t)p.ent_stride + p.col0;
+  const float* trow = p.ent + tidx * (int64_t)p.ent_stride + p.col0;
   const float* fixed = HEAD ? trow : hrow;
-  const float* relrow = p.rel + rid * (int64_t)p.rel_stride;
+  const float* relrow = p.rel + rid * (int64_t)p.rel_stride + p.col0;
   float scale = 1.f;
   if (p.stats) scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * __ldg(p.stats + 2));
   const bool do_pos = (p.gpos != nullptr) && blockIdx.y == 0;
@@ -268,9 +272,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
     if (active) {
       float a0[VEC], a1[VEC] = {}, rr0[VEC], rr1[VEC] = {};
       ld_global<VEC>(fixed + d, a0);
-      if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
+      if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.im_off + d, a1);
       ld_global<VEC>(relrow + d, rr0);
-      if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
+      if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.im_off + d, rr1);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         float r0, r1;
@@ -295,9 +299,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
           for (int u = 0; u < U; ++u) {
             const int k = jj + u * G;
             if (k < n) {
-              const float* row = p.ent + s_idx[k] * (int64_t)p.ent_stride;
+              const float* row = p.ent + s_idx[k] * (int64_t)p.ent_stride + p.col0;
               ld_global<VEC>(row + d, e0[u]);
-              if constexpr (T::NC == 2) ld_global<VEC>(row + p.D + d, e1[u]);
+              if constexpr (T::NC == 2) ld_global<VEC>(row + p.im_off + d, e1[u]);
             }
           }
 #pragma unroll
@@ -305,14 +309,14 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
             const int k = jj + u * G;
             if (k < n) {
               const float c = s_coef[k];
-              float* grow = p.grad_ent + s_idx[k] * (int64_t)p.ent_stride;
+              float* grow = p.grad_ent + s_idx[k] * (int64_t)p.g_ent_stride;
               float g0[VEC], g1[VEC];
 #pragma unroll
               for (int v = 0; v < VEC; ++v)
                 cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
                             dq0[v], dq1[v]);
               red_add<VEC>(grow + d, g0);
-              if constexpr (T::NC == 2) red_add<VEC>(grow + p.D + d, g1);
+              if constexpr (T::NC == 2) red_add<VEC>(grow + p.im_off + d, g1);
             }
           }
         }
@@ -348,9 +352,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       {
         float rr0[VEC], rr1[VEC] = {};
         ld_global<VEC>(fixed + d, a0);
-        if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.D + d, a1);
+        if constexpr (T::NC == 2) ld_global<VEC>(fixed + p.im_off + d, a1);
         ld_global<VEC>(relrow + d, rr0);
-        if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.D + d, rr1);
+        if constexpr (T::RC == 2) ld_global<VEC>(relrow + p.im_off + d, rr1);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
       }
@@ -362,10 +366,10 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       if (do_pos) {
         float t0[VEC], t1[VEC] = {};
         ld_global<VEC>(trow + d, t0);
-        if constexpr (T::NC == 2) ld_global<VEC>(trow + p.D + d, t1);
+        if constexpr (T::NC == 2) ld_global<VEC>(trow + p.im_off + d, t1);
         if constexpr (HEAD) {
           ld_global<VEC>(hrow + d, h0);
-          if constexpr (T::NC == 2) ld_global<VEC>(hrow + p.D + d, h1);
+          if constexpr (T::NC == 2) ld_global<VEC>(hrow + p.im_off + d, h1);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             float qp0, qp1;
@@ -399,19 +403,19 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
         }
         rel_bwd<M>(dr0, dr1, r0[v], r1[v], p.phase_div, gr0[v], gr1[v]);
       }
-      float* gh = p.grad_ent + hid * (int64_t)p.ent_stride;
-      float* gt = p.grad_ent + tidx * (int64_t)p.ent_stride;
-      float* gr = p.grad_rel + rid * (int64_t)p.rel_stride;
+      float* gh = p.grad_ent + hid * (int64_t)p.g_ent_stride;
+      float* gt = p.grad_ent + tidx * (int64_t)p.g_ent_stride;
+      float* gr = p.grad_rel + rid * (int64_t)p.g_rel_stride;
       if (!HEAD || do_pos) {
         red_add<VEC>(gh + d, gh0);
-        if constexpr (T::NC == 2) red_add<VEC>(gh + p.D + d, gh1);
+        if constexpr (T::NC == 2) red_add<VEC>(gh + p.g_im_off + d, gh1);
       }
       if (HEAD || do_pos) {
         red_add<VEC>(gt + d, gt0);
-        if constexpr (T::NC == 2) red_add<VEC>(gt + p.D + d, gt1);
+        if constexpr (T::NC == 2) red_add<VEC>(gt + p.g_im_off + d, gt1);
       }
       red_add<VEC>(gr + d, gr0);
-      if constexpr (T::RC == 2) red_add<VEC>(gr + p.D + d, gr1);
+      if constexpr (T::RC == 2) red_add<VEC>(gr + p.g_im_off + d, gr1);
     }
   }
 }
@@ -501,9 +505,13 @@ static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t s
   return KGE_OK;
 }
 
+// col0 / ncols select a column chunk of the hidden dim; ncols <= 0 means the whole row, in which case
+// the gradient buffers have the tables' own layout.  With a chunk, grad_ent / grad_rel are dense
+// [n_entity, NC*ncols] / [n_relation, RC*ncols] buffers holding just that chunk.
 static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B, const int64_t* neg,
                    int64_t K, const float* gpos, const float* gneg, const float* stats,
-                   const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st) {
+                   const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st,
+                   int col0 = 0, int ncols = 0) {
   BwdParams p{};
   p.ent = t->entity;
   p.rel = t->relation;
@@ -517,11 +525,18 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.grad_rel = grad_rel;
   p.B = (int)B;
   p.K = neg ? (int)K : 0;
-  p.D = t->hidden_dim;
+  const bool chunked = ncols > 0;
+  if (chunked && (col0 < 0 || col0 + ncols > t->hidden_dim)) return KGE_E_SIZE;
+  p.D = chunked ? ncols : t->hidden_dim;
+  p.col0 = chunked ? col0 : 0;
+  p.im_off = t->hidden_dim;
   p.ent_stride = t->hidden_dim * entity_comps(t->model);
   p.rel_stride = t->hidden_dim * relation_comps(t->model);
+  p.g_im_off = p.D;
+  p.g_ent_stride = p.D * entity_comps(t->model);
+  p.g_rel_stride = p.D * relation_comps(t->model);
   p.phase_div = host_phase_div(t->embedding_range);
-  const bool vec = can_vectorize(t, grad_ent, grad_rel);
+  const bool vec = can_vectorize(t, grad_ent, grad_rel) && (p.col0 % 4 == 0) && (p.D % 4 == 0);
   const int VEC = vec ? 4 : 1;
   const int chunks = (p.D + VEC - 1) / VEC;
   int tpg = 32;
@@ -535,7 +550,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   int ks = 1;
   if (p.K > 0) {
     const int fill = (4 * sm_count() + (int)B - 1) / (int)B;
-    const double tbl = 2.0 * (double)t->n_entity * p.ent_stride * sizeof(float);
+    const double tbl = 2.0 * (double)t->n_entity * p.g_ent_stride * sizeof(float);  // table + grad touched
     const int band = (int)(tbl / (64.0 * 1024 * 1024)) + 1;
     const int want = fill > band ? fill : band;
     const int maxks = (p.K + 31) / 32;
@@ -625,6 +640,20 @@ extern "C" int kge_score_bwd(const kge_tables_t* t, int mode, const int64_t* sam
                    grad_entity, grad_relation, (cudaStream_t)stream);
   return run_bwd(t, mode, sample, B, neg, K, nullptr, grad_scores, nullptr, nullptr, grad_entity,
                  grad_relation, (cudaStream_t)stream);
+}
+
+extern "C" int kge_fused_bwd_chunk(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
+                                   const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
+                                   const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,
+                                   float* grad_entity_chunk, float* grad_relation_chunk, kge_stream_t stream) {
+  int rc = validate_tables(t);
+  if (rc) return rc;
+  if (!sample || !neg || !coef_pos || !coef_neg || !stats || !grad_entity_chunk || !grad_relation_chunk)
+    return KGE_E_NULL;
+  if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX || ncols <= 0) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, grad_entity_chunk,
+                 grad_relation_chunk, (cudaStream_t)stream, col0, ncols);
 }
 
 extern "C" size_t kge_loss_workspace_bytes(int64_t B) {

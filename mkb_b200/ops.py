@@ -262,6 +262,29 @@ def fused_backward_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, st
     N.count_launch()
 
 
+def fused_backward_chunk_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, col0, ncols,
+                             g_ent_chunk, g_rel_chunk, grad_loss=None):
+    """K3 restricted to hidden-dim columns [col0, col0+ncols): ADDS into the dense chunk buffers."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    B, K = neg.shape
+    N.check(lib.kge_fused_bwd_chunk(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K,
+                                    N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats), N.ptr(grad_loss), col0, ncols,
+                                    N.ptr(g_ent_chunk), N.ptr(g_rel_chunk), N.stream_ptr(ent.device)),
+            "kge_fused_bwd_chunk")
+    N.count_launch()
+
+
+def adam_step_chunk(param, grad_chunk, exp_avg, exp_avg_sq, comps, ncols, col0, im_off, step, lr, beta1=0.9,
+                    beta2=0.999, eps=1e-8, zero_grad=True):
+    lib = N.load()
+    N.check(lib.kge_adam_step_chunk(N.ptr(param), N.ptr(grad_chunk), N.ptr(exp_avg), N.ptr(exp_avg_sq),
+                                    param.shape[0], comps, ncols, col0, param.shape[1], im_off, int(step), lr,
+                                    beta1, beta2, eps, int(bool(zero_grad)), N.stream_ptr(param.device)),
+            "kge_adam_step_chunk")
+    N.count_launch()
+
+
 # ---------------------------------------------------------------------------------------------
 # K4 sampler
 # ---------------------------------------------------------------------------------------------

@@ -460,3 +460,32 @@ def test_sorted_rows_are_the_same_multiset(sampler_cases):
     xa, xb = a.generate(s, "tail-batch").cpu().numpy(), b.generate(s, "tail-batch").cpu().numpy()
     np.testing.assert_array_equal(xa, np.sort(xb, axis=1))
     assert (np.diff(xa, axis=1) >= 0).all() and not (np.diff(xb, axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_chunked_backward_and_pipelined_trainer_match(model):
+    """Column-chunked backward (+ chunk Adam on a side stream) == the single-launch step."""
+    from mkb_b200.compose import DeviceTrainer
+
+    rng = np.random.RandomState(1)
+    Nn, R, D, B, K = 700, 9, 512, 48, 40
+    tri = np.unique(np.stack([rng.randint(Nn, size=6000), rng.randint(R, size=6000), rng.randint(Nn, size=6000)], 1), axis=0)
+    ents, rels = {i: i for i in range(Nn)}, {i: i for i in range(R)}
+    out = []
+    for chunks in (1, 4):
+        torch.manual_seed(3)
+        m = getattr(models, model)(hidden_dim=D, entities=ents, relations=rels, gamma=9.0).to(DEV)
+        ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=11)
+        tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, chunks=chunks)
+        assert len(tr.chunks) == (0 if chunks == 1 else 4)
+        losses_ = []
+        for step in range(6):
+            idx = np.random.RandomState(100 + step).choice(len(tri), B, replace=False)
+            w = torch.full((B,), 0.25, device=DEV)
+            tr.step(_t(tri[idx]), w, "head-batch" if step % 2 == 0 else "tail-batch")
+            losses_.append(tr.loss())
+        torch.cuda.synchronize()
+        out.append((m.entity_embedding.detach().clone(), m.relation_embedding.detach().clone(), losses_))
+    torch.testing.assert_close(out[1][0], out[0][0], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(out[1][1], out[0][1], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-5)
