@@ -232,7 +232,7 @@ def run_ours(args):
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev)
-    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, chunks=args.chunks)
+    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, mode=args.mode)
 
     # this rank's batches: disjoint slices of a seeded permutation of the training triples
     from mkb_b200.datasets.dataset import subsampling_weights
@@ -350,11 +350,18 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_name(cfg), "global_batch": B * world, "negatives": K,
-                "parallelism": f"dp{world}: replicated tables, all-reduce of 3 loss sums + dense grads" if dist else "single GPU",
+                "parallelism": "single GPU" if not dist else (
+                    f"dp{world}, replicated tables; batch-parallel forward, column-parallel backward over the "
+                    f"all-gathered global batch, fused Adam + all-gather through NVLink peer stores"
+                    if trainer.mode == "colpar" else
+                    f"dp{world}, replicated tables; all-reduce of 3 loss sums + dense gradients" + (
+                        f" [{trainer.mode_note}]" if trainer.mode_note else "")),
                 "l2": "working set per step (tables+grads+Adam moments = "
                       f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
-                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)" if not trainer.chunks
-                        else f"sample_negatives + fused_fwd + {len(trainer.chunks)} x [fused_bwd_chunk | all-reduce + adam chunk on a side stream]",
+                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
+                        if trainer.mode != "colpar" else
+                        f"sample_negatives + fused_fwd + all-gather(step records) + {world} x fused_bwd_chunk + "
+                        "2 x adam_slice_bcast",
                 "final_loss": final_loss,
             },
             "roofline": {
@@ -391,8 +398,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=None,
-                    help="column chunks of the pipelined backward/all-reduce/Adam (default: 1 on one GPU, 4 on several)")
+    ap.add_argument("--mode", default=None, choices=["colpar", "allreduce"],
+                    help="multi-GPU scheme of DeviceTrainer (default colpar: column-parallel backward + fused "
+                         "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

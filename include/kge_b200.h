@@ -196,6 +196,17 @@ int kge_adam_step_chunk(float* param, float* grad_chunk, float* exp_avg, float* 
                         int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
                         kge_stream_t stream);
 
+/* Column-parallel multi-GPU step (fused update + all-gather over NVLink peer memory): this rank owns
+ * columns [col0, col0+ncols) of every row.  grad_slice / exp_avg_slice / exp_avg_sq_slice are dense
+ * [rows, comps*ncols] slice buffers; param_replicas is a HOST array of n_replicas (<= 16) DEVICE
+ * pointers to the table on every GPU (peer-mapped, e.g. from torch symmetric memory), self_index the
+ * local one.  Reads the local replica, applies Adam, stores the new values into all replicas. */
+int kge_adam_slice_bcast(float* const* param_replicas, int32_t n_replicas, int32_t self_index,
+                         float* grad_slice, float* exp_avg_slice, float* exp_avg_sq_slice, int64_t rows,
+                         int32_t comps, int32_t ncols, int32_t col0, int32_t row_stride, int32_t im_off,
+                         int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
+                         kge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

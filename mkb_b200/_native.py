@@ -62,6 +62,9 @@ PROTOTYPES = {
     "kge_adam_step_chunk": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                       _P]),
+    "kge_adam_slice_bcast": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P, _I64, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I64, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_int, _P]),
     "kge_sample_negatives": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64,
                                        C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]),
     "kge_filter_pool": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,

@@ -1,14 +1,28 @@
-"""Device-resident training step: sampler -> fused forward -> fused backward -> dense Adam, five
-kernel launches on one stream, no host synchronisation and no allocation per step.
+"""Device-resident training step: sampler -> fused forward -> fused backward -> dense Adam on one
+stream, no host synchronisation and no allocation per step.
 
 This is the loop body of mkb/compose/pipeline.py:206-242 with every tensor the step touches kept in
 HBM (tables, gradients, Adam moments, the batch's negatives, per-score coefficients).  It is what
 ``Pipeline.learn`` reduces to when nothing on the step needs the host, and what ``bench.py`` times.
 
-Multi-GPU (one process per GPU, torch.distributed/NCCL): tables are replicated, each rank scores
-its own positives; the three loss sums are all-reduced between forward and backward so every rank
-normalises by the global sum of weights (losses/adversarial.py:28-30 over the global batch), and the
-dense gradients are all-reduced before the (replicated) Adam step.
+Multi-GPU (one process per GPU, torch.distributed/NCCL, tables replicated, rank r scores its own
+positives).  Two schemes:
+
+``colpar`` (default) — batch-parallel forward, COLUMN-parallel backward.
+    The backward is element-wise in the hidden dim, so instead of every rank producing a full dense
+    gradient that must be all-reduced (2 x table bytes over NVLink), rank r computes the gradient of
+    hidden-dim columns slice r for the GLOBAL batch: the per-score coefficients, negatives and triples
+    of all ranks are all-gathered (~3 MB per rank), each rank runs the chunked backward over them for
+    its columns only (same bytes as a single-GPU backward), applies Adam to its slice (1/G of the
+    optimizer work and state) and stores the updated slice into every replica through NVLink peer
+    pointers (`kge_adam_slice_bcast`: update + all-gather fused, 1 x table bytes over NVLink).
+    Needs the tables in torch symmetric memory; falls back to ``allreduce`` when that is unavailable.
+
+``allreduce`` — every rank computes the full gradient of its positives; one all-reduce of the flat
+    gradient buffer; replicated Adam.
+
+In both, the three loss sums are all-reduced between forward and backward so every rank normalises
+by the global sum of weights (losses/adversarial.py:28-30 over the global batch).
 """
 from __future__ import annotations
 
@@ -20,23 +34,34 @@ from . import parallel
 __all__ = ["DeviceTrainer"]
 
 
+def _column_slices(D, parts, align=32):
+    width = -(-D // parts // align) * align
+    out, col = [], 0
+    for _ in range(parts):
+        w = max(0, min(width, D - col))
+        out.append((col, w))
+        col += w
+    return out
+
+
 class DeviceTrainer:
     @classmethod
     def from_optimizer(cls, model, sampling, optimizer, alpha=0.5, max_batch=1024, **kw):
         """Adopt the hyper-parameters (and, if any, the moments) of a ``mkb_b200.optim.DenseAdam`` built
         over ``model.parameters()`` and keep that optimizer's state pointing at the trainer's buffers,
-        so ``optimizer.state_dict()`` stays meaningful after training."""
+        so ``optimizer.state_dict()`` stays meaningful after training (single-GPU / allreduce modes)."""
         group = optimizer.param_groups[0]
         t = cls(model, sampling, lr=group["lr"], betas=tuple(group["betas"]), eps=group["eps"], alpha=alpha,
                 max_batch=max_batch, **kw)
-        for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
-            st = optimizer.state[p]
-            if st:
-                m.copy_(st["exp_avg"])
-                v.copy_(st["exp_avg_sq"])
-                t.t = max(t.t, int(st["step"]))
-            st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, t.t
-        t._optimizer = optimizer
+        if t.mode != "colpar":
+            for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
+                st = optimizer.state[p]
+                if st:
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                    t.t = max(t.t, int(st["step"]))
+                st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, t.t
+            t._optimizer = optimizer
         return t
 
     def sync_optimizer_state(self):
@@ -46,81 +71,135 @@ class DeviceTrainer:
                 opt.state[p]["step"] = self.t
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
-                 process_group=None, distributed=False, chunks=None):
+                 process_group=None, distributed=False, mode=None):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
         self.model, self.sampling = model, sampling
         self.spec = model.spec
-        self.ent, self.rel = ent.data, rel.data
         self.dev = ent.device
         self.lr, self.betas, self.eps, self.alpha = lr, betas, eps, alpha
-        self.distributed = distributed
         self.group = process_group
-        K = sampling.size
-        f32 = dict(dtype=torch.float32, device=self.dev)
-        # Gradient storage.  chunks == 1: one flat buffer in the tables' layout.  chunks > 1: the hidden
-        # dim is cut into column chunks and the buffer is chunk-major ([entity chunk c | relation chunk c]
-        # contiguous), so the backward of chunk c, its all-reduce and its Adam update form a pipeline:
-        # while the main stream computes chunk c+1, a side stream reduces and applies chunk c.
+        self.world = torch.distributed.get_world_size(process_group) if distributed else 1
+        self.rank = torch.distributed.get_rank(process_group) if distributed else 0
+        self.distributed = distributed and self.world > 1
         D = model.hidden_dim
-        self.nc = self.ent.shape[1] // D
-        self.rc = self.rel.shape[1] // D
-        if chunks is None:
-            chunks = 4 if distributed else 1
-        if D % 4 != 0 or D < 128 * chunks:
-            chunks = 1
-        self.chunks = []
-        self._gflat = torch.zeros(self.ent.numel() + self.rel.numel(), **f32)
-        if chunks == 1:
-            self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
-            self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
-        else:
-            width = -(-D // chunks // 32) * 32
-            off, col = 0, 0
-            while col < D:
-                w = min(width, D - col)
-                ne, nr = self.ent.shape[0] * self.nc * w, self.rel.shape[0] * self.rc * w
-                flat = self._gflat[off: off + ne + nr]
-                self.chunks.append((col, w, flat, flat[:ne].view(self.ent.shape[0], self.nc * w),
-                                    flat[ne:].view(self.rel.shape[0], self.rc * w)))
-                off += ne + nr
-                col += w
-            self.side = torch.cuda.Stream(device=self.dev)
-            self._chunk_done = [torch.cuda.Event() for _ in self.chunks]
-        self.m_ent, self.v_ent = torch.zeros_like(self.ent), torch.zeros_like(self.ent)
-        self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
-        self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
-        self.coef_pos = torch.empty(max_batch, **f32)
-        self.coef_neg = torch.empty((max_batch, K), **f32)
+        self.D = D
+        self.nc = ent.shape[1] // D
+        self.rc = rel.shape[1] // D
+        K = sampling.size
+        self.max_batch, self.K = max_batch, K
+        f32 = dict(dtype=torch.float32, device=self.dev)
+
+        if mode is None:
+            mode = "colpar" if self.distributed else "single"
+        if not self.distributed:
+            mode = "single"
+        if mode == "colpar" and (D % 4 != 0 or D < 32 * self.world or self.world > 16):
+            mode = "allreduce"
+        self.mode_note = ""
+        if mode == "colpar":
+            try:
+                self._setup_symmetric_tables(model)
+            except Exception as e:  # no symmetric memory on this box / build
+                self.mode_note = f"colpar unavailable ({type(e).__name__}: {e}); using allreduce"
+                mode = "allreduce"
+        self.mode = mode
+        self.ent, self.rel = model.entity_embedding.data, model.relation_embedding.data
+
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.stats = torch.zeros(4, **f32)
         self.ws = torch.zeros(max(ops.N.load().kge_loss_workspace_bytes(max_batch), 64), dtype=torch.uint8,
                               device=self.dev)
-        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.max_batch, self.K = max_batch, K
-        self.t = 0
         self._csr = {m: sampling._csr("head" if m == "head-batch" else "tail", self.dev)
                      for m in ("head-batch", "tail-batch")}
-        self.hooks = None  # optional (pre_fwd, post_fwd, pre_bwd, post_bwd) event recorders for bench.py
+        self.t = 0
+        self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd] CUDA events (bench.py)
 
+        if mode == "colpar":
+            self._setup_colpar(f32)
+        else:
+            # one flat buffer for both gradients => a single all-reduce in the allreduce mode
+            self._gflat = torch.zeros(self.ent.numel() + self.rel.numel(), **f32)
+            self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
+            self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
+            self.m_ent, self.v_ent = torch.zeros_like(self.ent), torch.zeros_like(self.ent)
+            self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
+            self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
+            self.coef_pos = torch.empty(max_batch, **f32)
+            self.coef_neg = torch.empty((max_batch, K), **f32)
 
-    def step(self, sample, weight, mode):
-        """One optimisation step on a device-resident batch; returns the device loss scalar (a view
-        of the stats buffer, valid until the next step)."""
-        B = sample.shape[0]
-        if B > self.max_batch:
-            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
-        neg = self.neg[:B]
-        coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
+    # ------------------------------------------------------------------------------------------
+    # colpar set-up
+    # ------------------------------------------------------------------------------------------
+    def _setup_symmetric_tables(self, model):
+        """Move both tables into torch symmetric memory and exchange peer pointers (collective)."""
+        import torch.distributed._symmetric_memory as symm
+
+        group = self.group if self.group is not None else torch.distributed.group.WORLD
+        self._symm = []
+        self._replicas = []
+        for name in ("entity_embedding", "relation_embedding"):
+            p = getattr(model, name)
+            buf = symm.empty(*p.shape, dtype=torch.float32, device=self.dev)
+            buf.copy_(p.data)
+            hdl = symm.rendezvous(buf, group)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != buf.data_ptr():
+                raise RuntimeError("unexpected symmetric-memory pointer table")
+            p.data = buf
+            self._symm.append(hdl)
+            self._replicas.append(ptrs)
+        torch.cuda.synchronize(self.dev)
+        torch.distributed.barrier(group=self.group)
+
+    def _setup_colpar(self, f32):
+        B, K, G = self.max_batch, self.K, self.world
+        self.col0, self.ncols = _column_slices(self.D, G)[self.rank]
+        w = self.ncols
+        N_, R_ = self.ent.shape[0], self.rel.shape[0]
+        self.g_ent = torch.zeros(N_, self.nc * w, **f32)
+        self.g_rel = torch.zeros(R_, self.rc * w, **f32)
+        self.m_ent, self.v_ent = torch.zeros_like(self.g_ent), torch.zeros_like(self.g_ent)
+        self.m_rel, self.v_rel = torch.zeros_like(self.g_rel), torch.zeros_like(self.g_rel)
+        # per-rank step record, packed so ONE all-gather moves everything the backward needs
+        o_sample, o_neg = 0, B * 24
+        o_cpos = o_neg + B * K * 8
+        o_cneg = o_cpos + B * 4
+        rec = (o_cneg + B * K * 4 + 15) // 16 * 16
+        self._rec_all = torch.zeros(G * rec, dtype=torch.uint8, device=self.dev)
+        self._recs = []
+        for r in range(G):
+            base = self._rec_all[r * rec:(r + 1) * rec]
+            self._recs.append((base[o_sample:o_neg].view(torch.int64).view(B, 3),
+                               base[o_neg:o_cpos].view(torch.int64).view(B, K),
+                               base[o_cpos:o_cneg].view(torch.float32),
+                               base[o_cneg:o_cneg + B * K * 4].view(torch.float32).view(B, K)))
+        self._rec_local = self._rec_all[self.rank * rec:(self.rank + 1) * rec]
+        _, self.neg, self.coef_pos, self.coef_neg = self._recs[self.rank]
+        self._tiny = torch.zeros(1, **f32)
+
+    # ------------------------------------------------------------------------------------------
+    def _sample(self, sample, mode, neg):
         s = self.sampling
         if s.pool == "reference":  # the reference's host-drawn shared pool: 2K ids cross PCIe
             pool = torch.from_numpy(s._rng.randint(s.n_entity, size=self.K * 2).astype("int64")).to(
                 self.dev, non_blocking=True)
             ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg)
         else:
-            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status, neg,
-                                 sort_rows=s.sort_rows)
+            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status,
+                                 neg, sort_rows=s.sort_rows)
         s._calls += 1
+
+    def step(self, sample, weight, mode):
+        """One optimisation step on a device-resident batch; returns the device stats buffer
+        (S_p, S_n, W, local loss), valid until the next step."""
+        B = sample.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        neg = self.neg[:B]
+        coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
+        self._sample(sample, mode, neg)
         h = self.hooks
         if h:
             h[0].record()
@@ -130,39 +209,43 @@ class DeviceTrainer:
             h[1].record()
         if self.distributed:
             parallel.allreduce_loss_sums(self.stats, self.group)
-        if h:
-            h[2].record()
         self.t += 1
         b1, b2 = self.betas
-        if not self.chunks:
-            ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg,
-                                   self.stats, self.g_ent, self.g_rel)
-            if h:
-                h[3].record()
-            if self.distributed:
-                parallel.allreduce_gradients(self._gflat, self.group)
-            ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps,
-                          zero_grad=True)
-            ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps,
-                          zero_grad=True)
-            return self.stats
-        main = torch.cuda.current_stream(self.dev)
-        D = self.model.hidden_dim
-        for c, (col, w, flat, ge, gr) in enumerate(self.chunks):
-            ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg,
-                                         self.stats, col, w, ge, gr)
-            self._chunk_done[c].record(main)
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(self._chunk_done[c])
-                if self.distributed:
-                    parallel.allreduce_gradients(flat, self.group)
-                ops.adam_step_chunk(self.ent, ge, self.m_ent, self.v_ent, self.nc, w, col, D, self.t, self.lr,
-                                    b1, b2, self.eps)
-                ops.adam_step_chunk(self.rel, gr, self.m_rel, self.v_rel, self.rc, w, col, D, self.t, self.lr,
-                                    b1, b2, self.eps)
+        if self.mode == "colpar":
+            return self._step_colpar(sample, B, mode, h)
+        if h:
+            h[2].record()
+        ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
+                               self.g_ent, self.g_rel)
         if h:
             h[3].record()
-        main.wait_stream(self.side)
+        if self.distributed:
+            parallel.allreduce_gradients(self._gflat, self.group)
+        ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        return self.stats
+
+    def _step_colpar(self, sample, B, mode, h):
+        # (the stats all-reduce above doubles as the "every rank finished its forward" point, after
+        # which table columns may be overwritten by their owners)
+        self._recs[self.rank][0][:B].copy_(sample)
+        torch.distributed.all_gather_into_tensor(self._rec_all, self._rec_local, group=self.group)
+        if h:
+            h[2].record()
+        if self.ncols > 0:
+            for s_r, n_r, cp_r, cn_r in self._recs:  # the global batch, one source rank at a time
+                ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s_r[:B], n_r[:B], mode, cp_r[:B],
+                                             cn_r[:B], self.stats, self.col0, self.ncols, self.g_ent, self.g_rel)
+        if h:
+            h[3].record()
+        b1, b2 = self.betas
+        if self.ncols > 0:
+            for reps, g, m, v, comps, tbl in ((self._replicas[0], self.g_ent, self.m_ent, self.v_ent, self.nc, self.ent),
+                                              (self._replicas[1], self.g_rel, self.m_rel, self.v_rel, self.rc, self.rel)):
+                ops.adam_slice_bcast(reps, self.rank, g, m, v, tbl.shape[0], comps, self.ncols, self.col0,
+                                     tbl.shape[1], self.D, self.t, self.lr, b1, b2, self.eps, device=self.dev)
+        # every replica must hold every slice before anyone's next forward reads the tables
+        torch.distributed.all_reduce(self._tiny, group=self.group)
         return self.stats
 
     def loss(self):

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
                 cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
                             dq0[v], dq1[v]);
               red_add<VEC>(grow + d, g0);
-              if constexpr (T::NC == 2) red_add<VEC>(grow + p.im_off + d, g1);
+              if constexpr (T::NC == 2) red_add<VEC>(grow + p.g_im_off + d, g1);
             }
           }
         }

@@ -285,6 +285,18 @@ def adam_step_chunk(param, grad_chunk, exp_avg, exp_avg_sq, comps, ncols, col0, 
     N.count_launch()
 
 
+def adam_slice_bcast(replica_ptrs, self_index, grad_slice, m_slice, v_slice, rows, comps, ncols, col0, row_stride,
+                     im_off, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True, device=None):
+    """Adam on this rank's column slice, new values stored into every GPU's replica (peer pointers)."""
+    lib = N.load()
+    arr = (C.c_void_p * len(replica_ptrs))(*[int(p) for p in replica_ptrs])
+    N.check(lib.kge_adam_slice_bcast(arr, len(replica_ptrs), self_index, N.ptr(grad_slice), N.ptr(m_slice),
+                                     N.ptr(v_slice), rows, comps, ncols, col0, row_stride, im_off, int(step), lr,
+                                     beta1, beta2, eps, int(bool(zero_grad)), N.stream_ptr(device)),
+            "kge_adam_slice_bcast")
+    N.count_launch()
+
+
 # ---------------------------------------------------------------------------------------------
 # K4 sampler
 # ---------------------------------------------------------------------------------------------

@@ -463,29 +463,37 @@ def test_sorted_rows_are_the_same_multiset(sampler_cases):
 
 
 @pytest.mark.parametrize("model", MODELS)
-def test_chunked_backward_and_pipelined_trainer_match(model):
-    """Column-chunked backward (+ chunk Adam on a side stream) == the single-launch step."""
-    from mkb_b200.compose import DeviceTrainer
-
+@pytest.mark.parametrize("mode", MODES)
+def test_column_chunked_backward_and_adam_match_full(model, mode):
+    """kge_fused_bwd_chunk over the column chunks == kge_fused_bwd; kge_adam_step_chunk == kge_adam_step
+    (the building blocks of the column-parallel multi-GPU step), incl. uneven and narrow chunks."""
     rng = np.random.RandomState(1)
     Nn, R, D, B, K = 700, 9, 512, 48, 40
-    tri = np.unique(np.stack([rng.randint(Nn, size=6000), rng.randint(R, size=6000), rng.randint(Nn, size=6000)], 1), axis=0)
-    ents, rels = {i: i for i in range(Nn)}, {i: i for i in range(R)}
-    out = []
-    for chunks in (1, 4):
-        torch.manual_seed(3)
-        m = getattr(models, model)(hidden_dim=D, entities=ents, relations=rels, gamma=9.0).to(DEV)
-        ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=11)
-        tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, chunks=chunks)
-        assert len(tr.chunks) == (0 if chunks == 1 else 4)
-        losses_ = []
-        for step in range(6):
-            idx = np.random.RandomState(100 + step).choice(len(tri), B, replace=False)
-            w = torch.full((B,), 0.25, device=DEV)
-            tr.step(_t(tri[idx]), w, "head-batch" if step % 2 == 0 else "tail-batch")
-            losses_.append(tr.loss())
-        torch.cuda.synchronize()
-        out.append((m.entity_embedding.detach().clone(), m.relation_embedding.detach().clone(), losses_))
-    torch.testing.assert_close(out[1][0], out[0][0], rtol=1e-4, atol=1e-6)
-    torch.testing.assert_close(out[1][1], out[0][1], rtol=1e-4, atol=1e-6)
-    np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-5)
+    torch.manual_seed(3)
+    m = getattr(models, model)(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                               gamma=9.0).to(DEV)
+    ent, rel = m.entity_embedding.detach(), m.relation_embedding.detach()
+    ent.mul_(3.0)
+    s = _t(np.stack([rng.randint(Nn, size=B), rng.randint(R, size=B), rng.randint(Nn, size=B)], 1))
+    n = _t(rng.randint(Nn, size=(B, K)))
+    w = torch.full((B,), 0.25, device=DEV)
+    cp, cn = torch.empty(B, device=DEV), torch.empty(B, K, device=DEV)
+    stats, ws = torch.zeros(4, device=DEV), torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
+    ops.fused_forward_raw(m.spec, ent, rel, s, n, w, mode, 0.5, cp, cn, stats, ws)
+    ge, gr = torch.zeros_like(ent), torch.zeros_like(rel)
+    ops.fused_backward_raw(m.spec, ent, rel, s, n, mode, cp, cn, stats, ge, gr)
+    nc, rc = ent.shape[1] // D, rel.shape[1] // D
+    p1, p2 = ent.clone(), ent.clone()
+    m1, v1, m2, v2 = (torch.zeros_like(ent) for _ in range(4))
+    ops.adam_step(p1, ge.clone(), m1, v1, 3, 1e-3)
+    for col, wd in ((0, 128), (128, 256), (384, 96), (480, 32)):
+        gec, grc = torch.zeros(Nn, nc * wd, device=DEV), torch.zeros(R, rc * wd, device=DEV)
+        ops.fused_backward_chunk_raw(m.spec, ent, rel, s, n, mode, cp, cn, stats, col, wd, gec, grc)
+        ref_e = ge.view(Nn, nc, D)[:, :, col:col + wd].reshape(Nn, nc * wd)
+        ref_r = gr.view(R, rc, D)[:, :, col:col + wd].reshape(R, rc * wd)
+        assert (gec - ref_e).abs().max().item() <= 1e-5 * ref_e.abs().max().item()
+        assert (grc - ref_r).abs().max().item() <= 1e-5 * ref_r.abs().max().item()
+        ops.adam_step_chunk(p2, ref_e.contiguous(), m2, v2, nc, wd, col, D, 3, 1e-3)
+    torch.testing.assert_close(p2, p1, rtol=0, atol=0)
+    torch.testing.assert_close(m2, m1, rtol=0, atol=0)
+    torch.testing.assert_close(v2, v1, rtol=0, atol=0)
