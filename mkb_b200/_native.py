@@ -13,7 +13,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkge_b200.so")
+LIB_PATH = os.environ.get("KGE_B200_LIB") or os.path.join(_HERE, "lib", "libkge_b200.so")
 
 MODEL_IDS = {"TransE": 0, "DistMult": 1, "ComplEx": 2, "RotatE": 3}
 TAIL_BATCH, HEAD_BATCH = 0, 1

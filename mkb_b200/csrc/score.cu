@@ -21,6 +21,16 @@
 
 #include "kge_common.cuh"
 
+#ifndef KGE_FWD_R
+#define KGE_FWD_R 2  // candidate rows per warp iteration (shares each shared-memory read of q)
+#endif
+#ifndef KGE_FWD_MINB
+#define KGE_FWD_MINB 4  // resident CTAs per SM the forward kernel is compiled for (caps registers at 64)
+#endif
+#ifndef KGE_FWD_U
+#define KGE_FWD_U 2  // 16-byte chunks in flight per row per lane
+#endif
+
 namespace kge {
 
 struct FwdParams {
@@ -78,22 +88,29 @@ __global__ void __launch_bounds__(kThreads) score_pos_kernel(FwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one candidate row against the query in shared memory (one warp)
+// R candidate rows at a time against the query in shared memory (one warp).  Every query chunk read
+// from shared memory is used for R rows: the L1/TEX data path carries the global rows AND the
+// shared-memory reads of q, and ncu showed it (not L2 or HBM) saturating first with R = 1.
+// R * U row chunks (x NC components) of 16 bytes are in flight per lane.
 // ------------------------------------------------------------------------------------------------
-template <int M, int VEC>
-__device__ __forceinline__ float row_reduce(const float* __restrict__ row, const float* __restrict__ q,
-                                            int D, int Dp, int lane) {
+template <int M, int VEC, int R, int U>
+__device__ __forceinline__ void rows_reduce(const float* const (&row)[R], const float* __restrict__ q, int D,
+                                            int Dp, int lane, float (&out)[R]) {
   using T = Traits<M>;
-  constexpr int U = 4;  // row chunks in flight per lane
-  float acc = 0.f;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
   for (int d0 = lane * VEC; d0 < D; d0 += 32 * VEC * U) {
-    float e0[U][VEC], e1[U][VEC];
+    float e0[R][U][VEC], e1[R][U][VEC];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int d = d0 + u * 32 * VEC;
       if (d < D) {
-        ld_global<VEC>(row + d, e0[u]);
-        if constexpr (T::NC == 2) ld_global<VEC>(row + D + d, e1[u]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          ld_global<VEC>(row[r] + d, e0[r][u]);
+          if constexpr (T::NC == 2) ld_global<VEC>(row[r] + D + d, e1[r][u]);
+        }
       }
     }
 #pragma unroll
@@ -104,19 +121,22 @@ __device__ __forceinline__ float row_reduce(const float* __restrict__ row, const
         ld_shared<VEC>(q + d, q0);
         if constexpr (T::NC == 2) ld_shared<VEC>(q + Dp + d, q1);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          acc += cand_term<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f);
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            acc[r] += cand_term<M>(q0[v], q1[v], e0[r][u][v], T::NC == 2 ? e1[r][u][v] : 0.f);
       }
     }
   }
-  return warp_sum(acc);
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = warp_sum(acc[r]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward with candidates: grid = (B, K-slices); FUSED => K-slices == 1 and the loss is folded in
 // ------------------------------------------------------------------------------------------------
 template <int M, bool HEAD, int VEC, bool FUSED>
-__global__ void __launch_bounds__(kThreads, 4) score_neg_kernel(FwdParams p) {
+__global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[33];
@@ -184,14 +204,26 @@ __global__ void __launch_bounds__(kThreads, 4) score_neg_kernel(FwdParams p) {
     const int jmine = jb + lane * kWarps;
     const int64_t my_id = jmine < j1 ? negrow[jmine] : 0;
     const int cnt = min(32, (j1 - jb + kWarps - 1) / kWarps);
-    for (int m = 0; m < cnt; ++m) {
-      const int64_t id = __shfl_sync(kFull, my_id, m);
-      const float acc = row_reduce<M, VEC>(p.ent + id * (int64_t)p.ent_stride, q, p.D, p.Dp, lane);
+    constexpr int R = KGE_FWD_R, U = KGE_FWD_U;
+    for (int m = 0; m < cnt; m += R) {
+      const float* rows[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {  // rows past the end re-read the last valid one (result discarded)
+        const int64_t id = __shfl_sync(kFull, my_id, min(m + r, cnt - 1));
+        rows[r] = p.ent + id * (int64_t)p.ent_stride;
+      }
+      float acc[R];
+      rows_reduce<M, VEC, R, U>(rows, q, p.D, p.Dp, lane, acc);
       if (lane == 0) {
-        const int j = jb + m * kWarps;
-        const float s = finish_score<M>(acc, p.gamma);
-        if (p.neg_score) p.neg_score[i * (int64_t)p.K + j] = s;
-        if constexpr (FUSED) sc[j] = s;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (m + r < cnt) {
+            const int j = jb + (m + r) * kWarps;
+            const float s = finish_score<M>(acc[r], p.gamma);
+            if (p.neg_score) p.neg_score[i * (int64_t)p.K + j] = s;
+            if constexpr (FUSED) sc[j] = s;
+          }
+        }
       }
     }
   }
