@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
   }
 }
 
+// rank_tc.cu: tcgen05 (3xTF32) GEMM + fused rank count for the dot-product models
+int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
+                   const kge_filter_csr_t* filter, bool has_filter, const float* pos_score, const int64_t* seg,
+                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st);
+
 }  // namespace kge
 
 using namespace kge;
@@ -235,15 +240,18 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((Q + kTQ - 1) / kTQ), (unsigned)((p.N + kTE - 1) / kTE));
   if (grid.y > 65535) return KGE_E_SIZE;
-#define KGE_CASE(MM)                                                            \
-  case MM:                                                                      \
-    if (mode == KGE_HEAD_BATCH) {                                               \
-      rank_prepare_kernel<MM, true><<<(unsigned)Q, kThreads, 0, st>>>(p);       \
-      rank_tile_kernel<MM, true><<<grid, kThreads, 0, st>>>(p);                 \
-    } else {                                                                    \
-      rank_prepare_kernel<MM, false><<<(unsigned)Q, kThreads, 0, st>>>(p);      \
-      rank_tile_kernel<MM, false><<<grid, kThreads, 0, st>>>(p);                \
-    }                                                                           \
+  // dot-product models: GEMM on the tensor cores when the shape allows (otherwise the fp32 tiles)
+  const bool dot_model = (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT);
+#define KGE_CASE(MM)                                                                              \
+  case MM:                                                                                        \
+    if (mode == KGE_HEAD_BATCH) rank_prepare_kernel<MM, true><<<(unsigned)Q, kThreads, 0, st>>>(p); \
+    else rank_prepare_kernel<MM, false><<<(unsigned)Q, kThreads, 0, st>>>(p);                     \
+    if (dot_model &&                                                                              \
+        rank_tc_launch(p.qmat, p.ent, p.N, p.ent_stride, queries, p.Q, filter, p.has_filter != 0, \
+                       p.pos_score, p.seg, p.ranks, scores_out, mode == KGE_HEAD_BATCH, st) == KGE_OK) \
+      break;                                                                                      \
+    if (mode == KGE_HEAD_BATCH) rank_tile_kernel<MM, true><<<grid, kThreads, 0, st>>>(p);         \
+    else rank_tile_kernel<MM, false><<<grid, kThreads, 0, st>>>(p);                               \
     break;
   switch (t->model) {
     KGE_CASE(KGE_TRANSE)
