@@ -130,11 +130,16 @@ int kge_fused_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, i
  * [n_entity, NC*ncols] / [n_relation, RC*ncols] buffers for that chunk only, which makes each chunk's
  * gradient one contiguous region: the multi-GPU step all-reduces chunk c (and runs its Adam update,
  * kge_adam_step_chunk) while chunk c+1 is still being computed.  col0 and ncols must be multiples
- * of 4 for the vector path. */
+ * of 4 for the vector path.
+ * Multi-record batches: with n_records > 1 the sample / neg / coef_pos / coef_neg / stats pointers
+ * describe record 0 and record r lives record_stride_bytes further on (the packed, all-gathered
+ * step records of the G ranks); each record holds B positives and the global normaliser is the sum
+ * of the records' stats[2]. */
 int kge_fused_bwd_chunk(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
                         const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
                         const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,
-                        float* grad_entity_chunk, float* grad_relation_chunk, kge_stream_t stream);
+                        int32_t n_records, int64_t record_stride_bytes, float* grad_entity_chunk,
+                        float* grad_relation_chunk, kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  negative sampling on the device.  Replaces NegativeSampling.generate

@@ -21,8 +21,9 @@ positives).  Two schemes:
 ``allreduce`` — every rank computes the full gradient of its positives; one all-reduce of the flat
     gradient buffer; replicated Adam.
 
-In both, the three loss sums are all-reduced between forward and backward so every rank normalises
-by the global sum of weights (losses/adversarial.py:28-30 over the global batch).
+In both, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
+global batch): ``allreduce`` all-reduces the three loss sums between forward and backward; in
+``colpar`` they ride inside the all-gathered step records and the backward kernel sums them.
 """
 from __future__ import annotations
 
@@ -163,10 +164,13 @@ class DeviceTrainer:
         self.m_ent, self.v_ent = torch.zeros_like(self.g_ent), torch.zeros_like(self.g_ent)
         self.m_rel, self.v_rel = torch.zeros_like(self.g_rel), torch.zeros_like(self.g_rel)
         # per-rank step record, packed so ONE all-gather moves everything the backward needs
+        # (it also carries the rank's three loss sums, so no separate all-reduce is needed)
         o_sample, o_neg = 0, B * 24
         o_cpos = o_neg + B * K * 8
         o_cneg = o_cpos + B * 4
-        rec = (o_cneg + B * K * 4 + 15) // 16 * 16
+        o_stats = (o_cneg + B * K * 4 + 15) // 16 * 16
+        rec = o_stats + 16
+        self._rec_stride = rec
         self._rec_all = torch.zeros(G * rec, dtype=torch.uint8, device=self.dev)
         self._recs = []
         for r in range(G):
@@ -174,9 +178,11 @@ class DeviceTrainer:
             self._recs.append((base[o_sample:o_neg].view(torch.int64).view(B, 3),
                                base[o_neg:o_cpos].view(torch.int64).view(B, K),
                                base[o_cpos:o_cneg].view(torch.float32),
-                               base[o_cneg:o_cneg + B * K * 4].view(torch.float32).view(B, K)))
+                               base[o_cneg:o_cneg + B * K * 4].view(torch.float32).view(B, K),
+                               base[o_stats:o_stats + 16].view(torch.float32)))
         self._rec_local = self._rec_all[self.rank * rec:(self.rank + 1) * rec]
-        _, self.neg, self.coef_pos, self.coef_neg = self._recs[self.rank]
+        _, self.neg, self.coef_pos, self.coef_neg, self._stats_local = self._recs[self.rank]
+        self._stats_all = self._rec_all.view(G, rec)[:, o_stats:o_stats + 16].view(torch.float32)  # [G,4] strided
         self._tiny = torch.zeros(1, **f32)
 
     # ------------------------------------------------------------------------------------------
@@ -203,16 +209,17 @@ class DeviceTrainer:
         h = self.hooks
         if h:
             h[0].record()
+        colpar = self.mode == "colpar"
         ops.fused_forward_raw(self.spec, self.ent, self.rel, sample, neg, weight, mode, self.alpha, coef_pos,
-                              coef_neg, self.stats, self.ws)
+                              coef_neg, self._stats_local if colpar else self.stats, self.ws)
         if h:
             h[1].record()
-        if self.distributed:
-            parallel.allreduce_loss_sums(self.stats, self.group)
         self.t += 1
         b1, b2 = self.betas
-        if self.mode == "colpar":
+        if colpar:
             return self._step_colpar(sample, B, mode, h)
+        if self.distributed:
+            parallel.allreduce_loss_sums(self.stats, self.group)
         if h:
             h[2].record()
         ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
@@ -226,16 +233,18 @@ class DeviceTrainer:
         return self.stats
 
     def _step_colpar(self, sample, B, mode, h):
-        # (the stats all-reduce above doubles as the "every rank finished its forward" point, after
-        # which table columns may be overwritten by their owners)
+        # One all-gather moves every rank's step record (triples, negatives, coefficients, loss sums).
+        # It is also the "every rank finished its forward" point after which table columns may be
+        # overwritten by their owners.
         self._recs[self.rank][0][:B].copy_(sample)
         torch.distributed.all_gather_into_tensor(self._rec_all, self._rec_local, group=self.group)
         if h:
             h[2].record()
-        if self.ncols > 0:
-            for s_r, n_r, cp_r, cn_r in self._recs:  # the global batch, one source rank at a time
-                ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s_r[:B], n_r[:B], mode, cp_r[:B],
-                                             cn_r[:B], self.stats, self.col0, self.ncols, self.g_ent, self.g_rel)
+        if self.ncols > 0:  # the global batch (G records x B positives) in ONE launch, my columns only
+            s0, n0, cp0, cn0, st0 = self._recs[0]
+            ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s0[:B], n0[:B], mode, cp0[:B], cn0[:B], st0,
+                                         self.col0, self.ncols, self.g_ent, self.g_rel, n_records=self.world,
+                                         record_stride=self._rec_stride)
         if h:
             h[3].record()
         b1, b2 = self.betas
@@ -246,6 +255,7 @@ class DeviceTrainer:
                                      tbl.shape[1], self.D, self.t, self.lr, b1, b2, self.eps, device=self.dev)
         # every replica must hold every slice before anyone's next forward reads the tables
         torch.distributed.all_reduce(self._tiny, group=self.group)
+        torch.sum(self._stats_all, dim=0, out=self.stats)  # global (S_p, S_n, W, -) for loss()/logging
         return self.stats
 
     def loss(self):

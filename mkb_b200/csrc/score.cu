@@ -266,6 +266,11 @@ struct BwdParams {
   int g_ent_stride, g_rel_stride;
   int k_per_cta;
   int tpg;  // threads per group (multiple of 32, divides 256)
+  // Multi-record batches (the all-gathered global batch of the column-parallel multi-GPU step): the
+  // arrays above describe record 0, record r lives rec_stride bytes further on, each holds rec_B
+  // positives; stats of all records are summed for the global normaliser.  rec_B == 0: one record.
+  int rec_B, n_rec;
+  long long rec_stride;
   float phase_div;
 };
 
@@ -281,16 +286,33 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   const int tid = threadIdx.x;
   const int tpg = p.tpg, G = kThreads / tpg;
   const int grp = tid / tpg, lt = tid - grp * tpg;
-  const int64_t i = blockIdx.x;
-  const int64_t hid = p.sample[3 * i + 0], rid = p.sample[3 * i + 1], tidx = p.sample[3 * i + 2];
+  int64_t i = blockIdx.x;
+  size_t roff = 0;
+  if (p.rec_B > 0) {
+    const int64_t r = i / p.rec_B;
+    i -= r * p.rec_B;
+    roff = (size_t)r * (size_t)p.rec_stride;
+  }
+  const int64_t* smp = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.sample) + roff) + 3 * i;
+  const int64_t* negrow =
+      p.neg ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg) + roff) + i * (int64_t)p.K : nullptr;
+  const float* gnegrow =
+      p.gneg ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.gneg) + roff) + i * (int64_t)p.K : nullptr;
+  const int64_t hid = smp[0], rid = smp[1], tidx = smp[2];
   const float* hrow = p.ent + hid * (int64_t)p.ent_stride + p.col0;
   const float* trow = p.ent + tidx * (int64_t)p.ent_stride + p.col0;
   const float* fixed = HEAD ? trow : hrow;
   const float* relrow = p.rel + rid * (int64_t)p.rel_stride + p.col0;
   float scale = 1.f;
-  if (p.stats) scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * __ldg(p.stats + 2));
+  if (p.stats) {
+    float wsum = 0.f;
+    for (int r = 0; r < (p.rec_B > 0 ? p.n_rec : 1); ++r)
+      wsum += __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.stats) + (size_t)r * p.rec_stride) + 2);
+    scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * wsum);
+  }
   const bool do_pos = (p.gpos != nullptr) && blockIdx.y == 0;
-  const float cpos = do_pos ? scale * __ldg(p.gpos + i) : 0.f;
+  const float cpos =
+      do_pos ? scale * __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.gpos) + roff) + i) : 0.f;
   const int j0 = p.neg ? blockIdx.y * p.k_per_cta : 0;
   const int j1 = p.neg ? min(p.K, j0 + p.k_per_cta) : 0;
 
@@ -319,8 +341,8 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       const int n = min(kTileK, j1 - jt);
       __syncthreads();
       for (int k = tid; k < n; k += kThreads) {
-        s_idx[k] = p.neg[i * (int64_t)p.K + jt + k];
-        s_coef[k] = scale * p.gneg[i * (int64_t)p.K + jt + k];
+        s_idx[k] = negrow[jt + k];
+        s_coef[k] = scale * gnegrow[jt + k];
       }
       __syncthreads();
       if (active) {
@@ -543,7 +565,7 @@ static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t s
 static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B, const int64_t* neg,
                    int64_t K, const float* gpos, const float* gneg, const float* stats,
                    const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st,
-                   int col0 = 0, int ncols = 0) {
+                   int col0 = 0, int ncols = 0, int n_records = 1, long long record_stride = 0) {
   BwdParams p{};
   p.ent = t->entity;
   p.rel = t->relation;
@@ -557,6 +579,13 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.grad_rel = grad_rel;
   p.B = (int)B;
   p.K = neg ? (int)K : 0;
+  if (n_records > 1) {
+    p.rec_B = (int)B;
+    p.n_rec = n_records;
+    p.rec_stride = record_stride;
+  }
+  const int64_t total = B * (int64_t)(n_records > 1 ? n_records : 1);
+  if (total > INT32_MAX) return KGE_E_SIZE;
   const bool chunked = ncols > 0;
   if (chunked && (col0 < 0 || col0 + ncols > t->hidden_dim)) return KGE_E_SIZE;
   p.D = chunked ? ncols : t->hidden_dim;
@@ -581,7 +610,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   // of the entity table, so table + gradient of the active band stay L2-resident (~64 MB budget).
   int ks = 1;
   if (p.K > 0) {
-    const int fill = (4 * sm_count() + (int)B - 1) / (int)B;
+    const int fill = (4 * sm_count() + (int)total - 1) / (int)total;
     const double tbl = 2.0 * (double)t->n_entity * p.g_ent_stride * sizeof(float);  // table + grad touched
     const int band = (int)(tbl / (64.0 * 1024 * 1024)) + 1;
     const int want = fill > band ? fill : band;
@@ -591,7 +620,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   }
   p.k_per_cta = p.K > 0 ? (p.K + ks - 1) / ks : 0;
   if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
-  dim3 grid((unsigned)B, (unsigned)ks);
+  dim3 grid((unsigned)total, (unsigned)ks);
   const size_t smem = (size_t)(G - 1) * entity_comps(t->model) * tpg * VEC * sizeof(float);
 #define KGE_CASE(MM)                                                                       \
   case MM:                                                                                 \
@@ -677,15 +706,18 @@ extern "C" int kge_score_bwd(const kge_tables_t* t, int mode, const int64_t* sam
 extern "C" int kge_fused_bwd_chunk(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
                                    const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
                                    const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,
-                                   float* grad_entity_chunk, float* grad_relation_chunk, kge_stream_t stream) {
+                                   int32_t n_records, int64_t record_stride_bytes, float* grad_entity_chunk,
+                                   float* grad_relation_chunk, kge_stream_t stream) {
   int rc = validate_tables(t);
   if (rc) return rc;
   if (!sample || !neg || !coef_pos || !coef_neg || !stats || !grad_entity_chunk || !grad_relation_chunk)
     return KGE_E_NULL;
   if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX || ncols <= 0) return KGE_E_SIZE;
+  if (n_records < 1 || n_records > 64 || (n_records > 1 && (record_stride_bytes <= 0 || record_stride_bytes % 8)))
+    return KGE_E_SIZE;
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, grad_entity_chunk,
-                 grad_relation_chunk, (cudaStream_t)stream, col0, ncols);
+                 grad_relation_chunk, (cudaStream_t)stream, col0, ncols, n_records, record_stride_bytes);
 }
 
 extern "C" size_t kge_loss_workspace_bytes(int64_t B) {

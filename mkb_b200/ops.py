@@ -263,14 +263,16 @@ def fused_backward_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, st
 
 
 def fused_backward_chunk_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, col0, ncols,
-                             g_ent_chunk, g_rel_chunk, grad_loss=None):
-    """K3 restricted to hidden-dim columns [col0, col0+ncols): ADDS into the dense chunk buffers."""
+                             g_ent_chunk, g_rel_chunk, grad_loss=None, n_records=1, record_stride=0):
+    """K3 restricted to hidden-dim columns [col0, col0+ncols): ADDS into the dense chunk buffers.
+    ``n_records`` > 1: the tensors are record 0 of a packed multi-record batch (see the header)."""
     lib = N.load()
     tb = spec.struct(ent, rel)
     B, K = neg.shape
     N.check(lib.kge_fused_bwd_chunk(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K,
                                     N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats), N.ptr(grad_loss), col0, ncols,
-                                    N.ptr(g_ent_chunk), N.ptr(g_rel_chunk), N.stream_ptr(ent.device)),
+                                    n_records, record_stride, N.ptr(g_ent_chunk), N.ptr(g_rel_chunk),
+                                    N.stream_ptr(ent.device)),
             "kge_fused_bwd_chunk")
     N.count_launch()
 
