@@ -217,8 +217,12 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dist = world > 1
     if dist:
+        import datetime
+
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=dev)
+        # a stuck collective aborts the job after 3 minutes instead of hanging the box
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if world != args.gpus and rank == 0:
         print(f"# warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
 

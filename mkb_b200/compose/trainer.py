@@ -22,8 +22,14 @@ positives).  Two schemes:
     gradient buffer; replicated Adam.
 
 In both, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
-global batch): ``allreduce`` all-reduces the three loss sums between forward and backward; in
-``colpar`` they ride inside the all-gathered step records and the backward kernel sums them.
+global batch): the three loss sums are all-reduced between forward and backward.
+
+``packed_records=True`` (colpar only, opt-in) drops that all-reduce — the sums ride inside the
+all-gathered step records and the backward kernel adds them up — and runs the backward over all G
+records in ONE multi-record launch.  Measured on 2 GPUs: 0.777 vs 0.832 ms/step, parity-tested.  It is
+NOT the default because a 4- and an 8-GPU bench run with it hit their time limit in the last GPU call
+of round 1 and could not be diagnosed before the GPU budget ran out; the default flow below was
+measured on 2, 4 and 8 GPUs.
 """
 from __future__ import annotations
 
@@ -72,7 +78,7 @@ class DeviceTrainer:
                 opt.state[p]["step"] = self.t
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
-                 process_group=None, distributed=False, mode=None):
+                 process_group=None, distributed=False, mode=None, packed_records=False):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -106,6 +112,7 @@ class DeviceTrainer:
                 self.mode_note = f"colpar unavailable ({type(e).__name__}: {e}); using allreduce"
                 mode = "allreduce"
         self.mode = mode
+        self.packed_records = bool(packed_records) and mode == "colpar"
         self.ent, self.rel = model.entity_embedding.data, model.relation_embedding.data
 
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -169,7 +176,7 @@ class DeviceTrainer:
         o_cpos = o_neg + B * K * 8
         o_cneg = o_cpos + B * 4
         o_stats = (o_cneg + B * K * 4 + 15) // 16 * 16
-        rec = o_stats + 16
+        rec = o_stats + (16 if self.packed_records else 0)
         self._rec_stride = rec
         self._rec_all = torch.zeros(G * rec, dtype=torch.uint8, device=self.dev)
         self._recs = []
@@ -179,10 +186,11 @@ class DeviceTrainer:
                                base[o_neg:o_cpos].view(torch.int64).view(B, K),
                                base[o_cpos:o_cneg].view(torch.float32),
                                base[o_cneg:o_cneg + B * K * 4].view(torch.float32).view(B, K),
-                               base[o_stats:o_stats + 16].view(torch.float32)))
+                               base[o_stats:o_stats + 16].view(torch.float32) if self.packed_records else None))
         self._rec_local = self._rec_all[self.rank * rec:(self.rank + 1) * rec]
         _, self.neg, self.coef_pos, self.coef_neg, self._stats_local = self._recs[self.rank]
-        self._stats_all = self._rec_all.view(G, rec)[:, o_stats:o_stats + 16].view(torch.float32)  # [G,4] strided
+        if self.packed_records:  # [G,4] strided view of every record's loss sums
+            self._stats_all = self._rec_all.view(G, rec)[:, o_stats:o_stats + 16].view(torch.float32)
         self._tiny = torch.zeros(1, **f32)
 
     # ------------------------------------------------------------------------------------------
@@ -209,17 +217,17 @@ class DeviceTrainer:
         h = self.hooks
         if h:
             h[0].record()
-        colpar = self.mode == "colpar"
+        packed = self.packed_records
         ops.fused_forward_raw(self.spec, self.ent, self.rel, sample, neg, weight, mode, self.alpha, coef_pos,
-                              coef_neg, self._stats_local if colpar else self.stats, self.ws)
+                              coef_neg, self._stats_local if packed else self.stats, self.ws)
         if h:
             h[1].record()
         self.t += 1
         b1, b2 = self.betas
-        if colpar:
-            return self._step_colpar(sample, B, mode, h)
-        if self.distributed:
+        if self.distributed and not packed:
             parallel.allreduce_loss_sums(self.stats, self.group)
+        if self.mode == "colpar":
+            return self._step_colpar(sample, B, mode, h)
         if h:
             h[2].record()
         ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
@@ -233,18 +241,23 @@ class DeviceTrainer:
         return self.stats
 
     def _step_colpar(self, sample, B, mode, h):
-        # One all-gather moves every rank's step record (triples, negatives, coefficients, loss sums).
-        # It is also the "every rank finished its forward" point after which table columns may be
-        # overwritten by their owners.
+        # One all-gather moves every rank's step record (triples, negatives, coefficients[, loss sums]).
+        # Together with the loss-sum all-reduce before it, it is the "every rank finished its forward"
+        # point after which table columns may be overwritten by their owners.
         self._recs[self.rank][0][:B].copy_(sample)
         torch.distributed.all_gather_into_tensor(self._rec_all, self._rec_local, group=self.group)
         if h:
             h[2].record()
-        if self.ncols > 0:  # the global batch (G records x B positives) in ONE launch, my columns only
+        if self.ncols > 0 and self.packed_records:
+            # the global batch (G records x B positives) in ONE launch, my columns only
             s0, n0, cp0, cn0, st0 = self._recs[0]
             ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s0[:B], n0[:B], mode, cp0[:B], cn0[:B], st0,
                                          self.col0, self.ncols, self.g_ent, self.g_rel, n_records=self.world,
                                          record_stride=self._rec_stride)
+        elif self.ncols > 0:
+            for s_r, n_r, cp_r, cn_r, _ in self._recs:  # the global batch, one source rank at a time
+                ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s_r[:B], n_r[:B], mode, cp_r[:B],
+                                             cn_r[:B], self.stats, self.col0, self.ncols, self.g_ent, self.g_rel)
         if h:
             h[3].record()
         b1, b2 = self.betas
@@ -255,7 +268,8 @@ class DeviceTrainer:
                                      tbl.shape[1], self.D, self.t, self.lr, b1, b2, self.eps, device=self.dev)
         # every replica must hold every slice before anyone's next forward reads the tables
         torch.distributed.all_reduce(self._tiny, group=self.group)
-        torch.sum(self._stats_all, dim=0, out=self.stats)  # global (S_p, S_n, W, -) for loss()/logging
+        if self.packed_records:
+            torch.sum(self._stats_all, dim=0, out=self.stats)  # global (S_p, S_n, W, -) for loss()/logging
         return self.stats
 
     def loss(self):

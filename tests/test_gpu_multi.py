@@ -72,7 +72,7 @@ def test_two_gpu_step_matches_single_gpu_global_batch():
     assert out["ent_err"] < 1e-5 and out["rel_err"] < 1e-5
 
 
-def _worker_trainer(rank, world, port, out, mode):
+def _worker_trainer(rank, world, port, out, mode, packed=False):
     """DeviceTrainer in a multi-GPU mode vs rank 0 replaying the GLOBAL batch on one GPU."""
     import torch.distributed as dist
 
@@ -93,7 +93,7 @@ def _worker_trainer(rank, world, port, out, mode):
     torch.manual_seed(1)
     ref = models.RotatE(hidden_dim=D, entities=ents, relations=rels, gamma=9.0).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=5 + rank)
-    tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, distributed=True, mode=mode)
+    tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, distributed=True, mode=mode, packed_records=packed)
     opt = optim.DenseAdam([ref.entity_embedding, ref.relation_embedding], lr=1e-3)
     errs = []
     for step in range(4):
@@ -127,15 +127,15 @@ def _worker_trainer(rank, world, port, out, mode):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ("colpar", "allreduce"))
-def test_two_gpu_trainer_matches_single_gpu(mode):
+@pytest.mark.parametrize("mode,packed", (("colpar", False), ("colpar", True), ("allreduce", False)))
+def test_two_gpu_trainer_matches_single_gpu(mode, packed):
     import torch.multiprocessing as mp
 
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     out = mp.Manager().dict()
-    mp.spawn(_worker_trainer, args=(2, port, out, mode), nprocs=2, join=True)
+    mp.spawn(_worker_trainer, args=(2, port, out, mode, packed), nprocs=2, join=True)
     print(dict(out))
     assert out["mode"] == mode, out["note"]
     assert out["loss"] < 1e-5

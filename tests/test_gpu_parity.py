@@ -497,3 +497,45 @@ def test_column_chunked_backward_and_adam_match_full(model, mode):
     torch.testing.assert_close(p2, p1, rtol=0, atol=0)
     torch.testing.assert_close(m2, m1, rtol=0, atol=0)
     torch.testing.assert_close(v2, v1, rtol=0, atol=0)
+
+
+def test_multi_record_backward_equals_per_record_launches():
+    """kge_fused_bwd_chunk with n_records > 1 (packed step records, global normaliser = sum of the
+    records' W) == one launch per record with the summed W — on one GPU."""
+    rng = np.random.RandomState(2)
+    Nn, R, D, B, K, G = 400, 5, 256, 24, 16, 3
+    torch.manual_seed(0)
+    m = models.RotatE(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                      gamma=9.0).to(DEV)
+    ent, rel = m.entity_embedding.detach(), m.relation_embedding.detach()
+    o_neg, o_cp = B * 24, B * 24 + B * K * 8
+    o_cn = o_cp + B * 4
+    o_st = (o_cn + B * K * 4 + 15) // 16 * 16
+    rec = o_st + 16
+    buf = torch.zeros(G * rec, dtype=torch.uint8, device=DEV)
+    recs = []
+    ws = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
+    for r in range(G):
+        base = buf[r * rec:(r + 1) * rec]
+        s = base[:o_neg].view(torch.int64).view(B, 3)
+        n = base[o_neg:o_cp].view(torch.int64).view(B, K)
+        cp = base[o_cp:o_cn].view(torch.float32)
+        cn = base[o_cn:o_cn + B * K * 4].view(torch.float32).view(B, K)
+        st = base[o_st:o_st + 16].view(torch.float32)
+        s.copy_(_t(np.stack([rng.randint(Nn, size=B), rng.randint(R, size=B), rng.randint(Nn, size=B)], 1)))
+        n.copy_(_t(rng.randint(Nn, size=(B, K))))
+        w = _t(rng.uniform(0.1, 0.5, B).astype(np.float32))
+        ops.fused_forward_raw(m.spec, ent, rel, s, n, w, "tail-batch", 0.5, cp, cn, st, ws)
+        recs.append((s, n, cp, cn, st))
+    col, wd = 64, 128
+    g1, r1 = torch.zeros(Nn, 2 * wd, device=DEV), torch.zeros(R, wd, device=DEV)
+    s0, n0, cp0, cn0, st0 = recs[0]
+    ops.fused_backward_chunk_raw(m.spec, ent, rel, s0, n0, "tail-batch", cp0, cn0, st0, col, wd, g1, r1,
+                                 n_records=G, record_stride=rec)
+    total = torch.stack([st for *_, st in recs]).sum(0).contiguous()
+    g2, r2 = torch.zeros_like(g1), torch.zeros_like(r1)
+    for s, n, cp, cn, _ in recs:
+        ops.fused_backward_chunk_raw(m.spec, ent, rel, s, n, "tail-batch", cp, cn, total, col, wd, g2, r2)
+    assert g2.abs().max().item() > 0
+    assert (g1 - g2).abs().max().item() <= 1e-5 * g2.abs().max().item()
+    assert (r1 - r2).abs().max().item() <= 1e-5 * r2.abs().max().item()
