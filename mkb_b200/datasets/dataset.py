@@ -110,18 +110,40 @@ class Dataset:
         return {r: i for i, r in enumerate(dict.fromkeys([r for _, r, _ in self.true_triples]))}
 
     # -- iteration -----------------------------------------------------------------------------
-    def _order(self):
-        """One epoch's visiting order for one loader.  Mirrors the RNG consumption of
-        DataLoader(shuffle=True, num_workers>0): a base-seed draw, a sampler-seed draw, then
-        randperm on a private generator."""
+    # One epoch's visiting order for a loader, drawn the way torch's DataLoader(shuffle=True) does it so
+    # a seeded run visits the same batches as the reference: creating the loader iterator draws a base
+    # seed from the global RNG; the RandomSampler draws its own seed and runs randperm on a private
+    # generator.  With worker processes (the reference's default num_workers=1) the sampler is advanced
+    # while the iterator is being built (index prefetch), so the two draws are back to back per loader;
+    # in the single-process case the sampler seed is drawn lazily at the first next(), i.e. after BOTH
+    # loader iterators of zip(head, tail) exist.
+    @staticmethod
+    def _draw_seed():
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
+    def _perm(self, seed):
         n = self._triples.shape[0]
-        if not self.shuffle:
-            return torch.arange(n)
-        torch.empty((), dtype=torch.int64).random_()
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
         g = torch.Generator()
         g.manual_seed(seed)
         return torch.randperm(n, generator=g)
+
+    def _order(self):
+        n = self._triples.shape[0]
+        if not self.shuffle:
+            return torch.arange(n)
+        self._draw_seed()  # the iterator's base seed
+        return self._perm(self._draw_seed())
+
+    def _epoch_orders(self):
+        """(head order, tail order) for one pass of __iter__."""
+        n = self._triples.shape[0]
+        if not self.shuffle:
+            return torch.arange(n), torch.arange(n)
+        if self.num_workers and self.num_workers > 0:
+            return self._order(), self._order()
+        self._draw_seed()
+        self._draw_seed()
+        return self._perm(self._draw_seed()), self._perm(self._draw_seed())
 
     def _batches(self, mode, order):
         order = order.to(self._triples.device)
@@ -142,8 +164,9 @@ class Dataset:
                        "mode": mode}
 
     def __iter__(self):
-        head = self._batches("head-batch", self._order())
-        tail = self._batches("tail-batch", self._order())
+        head_order, tail_order = self._epoch_orders()
+        head = self._batches("head-batch", head_order)
+        tail = self._batches("tail-batch", tail_order)
         for hb, tb in zip(head, tail):
             yield hb
             yield tb

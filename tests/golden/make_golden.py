@@ -329,8 +329,32 @@ def gen_eval_doctest():
     print("eval_doctest", len(out), m)
 
 
+def gen_loader_order():
+    """Batch order of the reference's Dataset(shuffle=True) under a fixed torch seed, for both
+    DataLoader regimes (worker process / in-process), two epochs each."""
+    out = {}
+    rng = np.random.RandomState(0)
+    tri = sorted({(int(rng.randint(50)), int(rng.randint(3)), int(rng.randint(50))) for _ in range(300)})
+    ents, rels = {i: i for i in range(50)}, {i: i for i in range(3)}
+    out["triples"] = np.array(tri, dtype=np.int64)
+    for nw in (1, 0):
+        torch.manual_seed(123)
+        ds = datasets.Dataset(train=tri, entities=ents, relations=rels, batch_size=32, shuffle=True, seed=42,
+                              num_workers=nw)
+        for epoch in range(2):
+            batches = list(ds)
+            out[f"nw{nw}/epoch{epoch}/n"] = np.int64(len(batches))
+            for i, d in enumerate(batches):
+                out[f"nw{nw}/epoch{epoch}/b{i}"] = _np(d["sample"])
+                out[f"nw{nw}/epoch{epoch}/m{i}"] = np.array(d["mode"])
+    np.savez_compressed(os.path.join(HERE, "loader_order.npz"), **out)
+    print("loader_order", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc"]
+    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader"]
+    if "loader" in which:
+        gen_loader_order()
     if "step" in which:
         gen_step_cases()
     if "pins" in which:

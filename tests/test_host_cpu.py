@@ -131,3 +131,22 @@ def test_dataset_builds_mappings_like_reference():
     assert ds.entities == {"mkb": 0, "github": 1, "library": 2, "tool": 3}
     assert ds.relations == {"is_a": 0, "is_on": 1}
     assert ds.train == [(0, 0, 2), (1, 0, 3), (0, 1, 1)]
+
+
+@pytest.mark.parametrize("num_workers", (1, 0))
+def test_shuffled_batches_match_the_reference_loader(num_workers):
+    """datasets.Dataset(shuffle=True) consumes torch's RNG like the reference's two DataLoaders, so a
+    seeded run sees the same batches in the same order (fixture: tests/golden/make_golden.py loader)."""
+    from conftest import load_golden
+
+    g = load_golden("loader_order.npz")
+    tri = [tuple(int(x) for x in r) for r in g["triples"]]
+    torch.manual_seed(123)
+    ds = datasets.Dataset(train=tri, entities={i: i for i in range(50)}, relations={i: i for i in range(3)},
+                          batch_size=32, shuffle=True, seed=42, num_workers=num_workers)
+    for epoch in range(2):
+        batches = list(ds)
+        assert len(batches) == int(g[f"nw{num_workers}/epoch{epoch}/n"])
+        for i, d in enumerate(batches):
+            np.testing.assert_array_equal(d["sample"].numpy(), g[f"nw{num_workers}/epoch{epoch}/b{i}"])
+            assert d["mode"] == str(g[f"nw{num_workers}/epoch{epoch}/m{i}"])
