@@ -236,7 +236,10 @@ def run_ours(args):
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev)
-    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, mode=args.mode)
+    topts = {"mode": args.mode}
+    if args.virtual_shards:
+        topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
+    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
 
     # this rank's batches: disjoint slices of a seeded permutation of the training triples
     from mkb_b200.datasets.dataset import subsampling_weights
@@ -300,7 +303,7 @@ def run_ours(args):
     ds_warm = host_dataset(graph[order[: max(warmup // 2, 2)].reshape(-1)])
     ds_time = host_dataset(graph[order[warmup: warmup + half].reshape(-1)])
     e2e_steps = 2 * half
-    pipe = compose.Pipeline(epochs=1, device=dev)
+    pipe = compose.Pipeline(epochs=1, device=dev, trainer_options=topts)
     sys.stderr, _err = open(os.devnull, "w"), sys.stderr  # tqdm's bar
     try:
         pipe.learn(model=model2, dataset=ds_warm, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
@@ -354,16 +357,25 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_name(cfg), "global_batch": B * world, "negatives": K,
-                "parallelism": "single GPU" if not dist else (
+                "parallelism": (
+                    "single GPU" if trainer.mode != "rowshard" else
+                    f"single GPU, entity table in {trainer.n_shards} block-cyclic row shards (all local)")
+                if not dist else (
                     f"dp{world}, replicated tables; batch-parallel forward, column-parallel backward over the "
                     f"all-gathered global batch, fused Adam + all-gather through NVLink peer stores"
                     if trainer.mode == "colpar" else
+                    f"dp{world}, entity table row-sharded block-cyclically over the GPUs (1/{world} of table, gradient "
+                    f"and Adam state each); remote rows gathered by P2P loads, row gradients added into the owner's "
+                    f"shard by system-scope vector REDs over NVLink; relation gradient all-reduced"
+                    if trainer.mode == "rowshard" else
                     f"dp{world}, replicated tables; all-reduce of 3 loss sums + dense gradients" + (
                         f" [{trainer.mode_note}]" if trainer.mode_note else "")),
                 "l2": "working set per step (tables+grads+Adam moments = "
                       f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
                 "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
-                        if trainer.mode != "colpar" else
+                        if trainer.mode in ("single", "allreduce") else
+                        "sample_negatives + fused_fwd_sharded + fused_bwd_sharded + adam(own shard(s)) + adam(relation)"
+                        if trainer.mode == "rowshard" else
                         f"sample_negatives + fused_fwd + all-gather(step records) + {world} x fused_bwd_chunk + "
                         "2 x adam_slice_bcast",
                 "final_loss": final_loss,
@@ -402,9 +414,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default=None, choices=["colpar", "allreduce"],
+    ap.add_argument("--mode", default=None, choices=["colpar", "allreduce", "rowshard"],
                     help="multi-GPU scheme of DeviceTrainer (default colpar: column-parallel backward + fused "
-                         "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce)")
+                         "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce; rowshard: "
+                         "entity table row-sharded over the GPUs, P2P row gathers + remote gradient REDs)")
+    ap.add_argument("--virtual-shards", type=int, default=0,
+                    help="single GPU only: run the row-sharded kernels with this many local shards")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -142,6 +142,50 @@ int kge_fused_bwd_chunk(const kge_tables_t* tables, int mode, const int64_t* sam
                         float* grad_relation_chunk, kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  row-sharded entity table: K2 / K3 with every entity row resolved through a table of shard base
+ *     pointers (BASELINE config 4 "entity table row-sharded across 4 x B200 with P2P
+ *     remote-row gather").  Replaces the same reference code as K2 / K3 — index_select gathers of
+ *     mkb/models/base.py:167-205 and their dense index_add_ backward — for a table that is spread over
+ *     the HBM of several GPUs.
+ * Layout: block-cyclic.  Entity e lives on shard e % n_shards at local row e / n_shards, so shard s is
+ *     the fp32 row-major matrix [ceil((n_entity - s) / n_shards), entity_dim].  entity[s] / grad_entity[s]
+ *     are DEVICE pointers valid on the calling GPU: local memory for its own shard, peer mappings
+ *     (cudaIpc / torch symmetric memory over NVLink) for the others.  Remote rows are read with plain
+ *     16-byte loads; row gradients are added into the OWNER's gradient shard with system-scope vector
+ *     reductions (red.relaxed.sys.global.add.v4.f32) performed by the owner's L2.
+ * tables->entity is ignored (may be NULL); tables->n_entity is the GLOBAL entity count (< 2^31);
+ *     the relation table and its gradient stay replicated / local (the caller all-reduces
+ *     grad_relation).  hidden_dim must be a multiple of 4 and every shard pointer 16-byte aligned
+ *     (KGE_E_UNSUPPORTED / KGE_E_ALIGN otherwise).  scalar_red != 0 issues 4-byte instead of 16-byte
+ *     reductions (debugging aid).
+ * Synchronisation is the caller's: all ranks' kge_fused_bwd_sharded must have completed before an
+ *     owner consumes its gradient shard, and owners must have finished updating their table shard
+ *     before anyone's next forward reads it.
+ * ------------------------------------------------------------------------------------------- */
+#define KGE_MAX_SHARDS 16
+typedef struct kge_shards {
+  const float* entity[KGE_MAX_SHARDS];
+  float* grad_entity[KGE_MAX_SHARDS]; /* backward only */
+  int32_t n_shards;
+  int32_t scalar_red;
+} kge_shards_t;
+
+int kge_fused_fwd_sharded(const kge_tables_t* tables, const kge_shards_t* shards, int mode,
+                          const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                          const float* weight, float alpha, float* pos_score, float* neg_score,
+                          float* coef_pos, float* coef_neg, float* stats, void* workspace,
+                          kge_stream_t stream);
+int kge_fused_bwd_sharded(const kge_tables_t* tables, const kge_shards_t* shards, int mode,
+                          const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                          const float* coef_pos, const float* coef_neg, const float* stats,
+                          const float* grad_loss, float* grad_relation, kge_stream_t stream);
+/* Unfused scores through the shard table (model(sample) / model(sample, negative_sample, mode) for a
+ * row-sharded model; also what a sharded evaluation uses): same contract as kge_score_fwd. */
+int kge_score_fwd_sharded(const kge_tables_t* tables, const kge_shards_t* shards, int mode,
+                          const int64_t* sample, int64_t B, const int64_t* neg, int64_t K, float* scores,
+                          kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K4  negative sampling on the device.  Replaces NegativeSampling.generate
  *     (mkb/sampling/negative_sampling.py:158-201) and the dictionaries of positive_triples (:7-28),
  *     which become two CSR filters keyed by  relation * n_entity + fixed_entity:

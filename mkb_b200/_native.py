@@ -41,6 +41,18 @@ class KgeFilterCsr(C.Structure):
     ]
 
 
+MAX_SHARDS = 16  # KGE_MAX_SHARDS
+
+
+class KgeShards(C.Structure):
+    _fields_ = [
+        ("entity", C.c_void_p * MAX_SHARDS),
+        ("grad_entity", C.c_void_p * MAX_SHARDS),
+        ("n_shards", C.c_int32),
+        ("scalar_red", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/kge_b200.h declaration by declaration
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -65,6 +77,12 @@ PROTOTYPES = {
     "kge_adam_slice_bcast": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P, _I64, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I64, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_int, _P]),
+    "kge_fused_fwd_sharded": (C.c_int, [C.POINTER(KgeTables), C.POINTER(KgeShards), C.c_int, _P, _I64, _P, _I64,
+                                        _P, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "kge_fused_bwd_sharded": (C.c_int, [C.POINTER(KgeTables), C.POINTER(KgeShards), C.c_int, _P, _I64, _P, _I64,
+                                        _P, _P, _P, _P, _P, _P]),
+    "kge_score_fwd_sharded": (C.c_int, [C.POINTER(KgeTables), C.POINTER(KgeShards), C.c_int, _P, _I64, _P, _I64,
+                                        _P, _P]),
     "kge_sample_negatives": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64,
                                        C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]),
     "kge_filter_pool": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,

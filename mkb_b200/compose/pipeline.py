@@ -43,10 +43,13 @@ class _RollingMean:
 
 class Pipeline:
     def __init__(self, epochs, eval_every=2000, early_stopping_rounds=3, device="cpu", fused=True,
-                 loss_every=1):
+                 loss_every=1, trainer_options=None):
         """``fused=False`` forces the generic three-call loop.  ``loss_every`` > 1 reads the loss back
         to the host only every that many steps (the reference's ``error.item()`` at pipeline.py:242 is
-        a device sync per step); 1 keeps the reference behaviour."""
+        a device sync per step); 1 keeps the reference behaviour.  ``trainer_options`` are keyword
+        arguments for the device-resident ``DeviceTrainer`` (e.g. ``{"mode": "rowshard"}`` to row-shard
+        the entity table over the GPUs of the process group)."""
+        self.trainer_options = dict(trainer_options or {})
         self.epochs = epochs
         self.eval_every = eval_every
         self.early_stopping_rounds = early_stopping_rounds
@@ -80,7 +83,8 @@ class Pipeline:
         key = (id(model), id(sampling), id(optimizer), float(loss.alpha), int(dataset.batch_size), multi)
         if getattr(self, "_trainer_key", None) != key:  # keep buffers across learn() calls
             self._trainer = DeviceTrainer.from_optimizer(model, sampling, optimizer, alpha=loss.alpha,
-                                                         max_batch=int(dataset.batch_size), distributed=multi)
+                                                         max_batch=int(dataset.batch_size), distributed=multi,
+                                                         **self.trainer_options)
             self._trainer_key = key
         return self._trainer
 
@@ -105,6 +109,7 @@ class Pipeline:
         if pending is not None:
             self._record_loss(pending, host, done, bar, epoch)
         trainer.sync_optimizer_state()
+        trainer.sync_model()  # rowshard: gather the trained shards back into model.entity_embedding
 
     def _record_loss(self, slot, host, done, bar, epoch):
         done[slot].synchronize()

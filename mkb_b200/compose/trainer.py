@@ -21,7 +21,20 @@ positives).  Two schemes:
 ``allreduce`` — every rank computes the full gradient of its positives; one all-reduce of the flat
     gradient buffer; replicated Adam.
 
-In both, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
+``rowshard`` (opt-in; SURVEY §8(e), BASELINE config 4) — the entity table is ROW-sharded block-cyclically
+    (entity e on rank e % G, local row e / G), so each GPU holds 1/G of the table, of its gradient and of
+    the Adam moments: the scheme for tables that do not fit one GPU's HBM.  The forward gathers remote
+    rows with plain loads through NVLink peer pointers (`kge_fused_fwd_sharded`); the backward adds row
+    gradients into the OWNER's gradient shard with system-scope vector reductions over NVLink
+    (`kge_fused_bwd_sharded`); the relation table (<= 237 rows) stays replicated and its gradient is
+    all-reduced, which doubles as the "every rank's backward has landed" point; each rank then runs Adam
+    on its shard only, and a 4-byte all-reduce orders the next forward behind every owner's update.
+    ``virtual_shards=G`` runs the same kernels in ONE process with all G shards on this GPU (how the
+    single-GPU tests and benches exercise the sharded addressing).  At the configs of BASELINE.json the
+    tables fit one GPU many times over and (G-1)/G of all gathers would cross NVLink (~8x slower than
+    HBM), so this is not the default; see DESIGN.md §6.
+
+In all of them, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
 global batch): the three loss sums are all-reduced between forward and backward.
 
 ``packed_records=True`` (colpar only, opt-in) drops that all-reduce — the sums ride inside the
@@ -60,7 +73,7 @@ class DeviceTrainer:
         group = optimizer.param_groups[0]
         t = cls(model, sampling, lr=group["lr"], betas=tuple(group["betas"]), eps=group["eps"], alpha=alpha,
                 max_batch=max_batch, **kw)
-        if t.mode != "colpar":
+        if t.mode not in ("colpar", "rowshard"):
             for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
                 st = optimizer.state[p]
                 if st:
@@ -78,7 +91,8 @@ class DeviceTrainer:
                 opt.state[p]["step"] = self.t
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
-                 process_group=None, distributed=False, mode=None, packed_records=False):
+                 process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,
+                 scalar_red=False):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -98,9 +112,12 @@ class DeviceTrainer:
         self.max_batch, self.K = max_batch, K
         f32 = dict(dtype=torch.float32, device=self.dev)
 
+        self.virtual_shards = int(virtual_shards) if virtual_shards else 0
+        if self.virtual_shards and self.distributed:
+            raise ValueError("virtual_shards is a single-process mode")
         if mode is None:
-            mode = "colpar" if self.distributed else "single"
-        if not self.distributed:
+            mode = "rowshard" if self.virtual_shards else ("colpar" if self.distributed else "single")
+        if not self.distributed and mode != "rowshard":
             mode = "single"
         if mode == "colpar" and (D % 4 != 0 or D < 32 * self.world or self.world > 16):
             mode = "allreduce"
@@ -124,7 +141,9 @@ class DeviceTrainer:
         self.t = 0
         self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd] CUDA events (bench.py)
 
-        if mode == "colpar":
+        if mode == "rowshard":
+            self._setup_rowshard(model, f32, scalar_red)
+        elif mode == "colpar":
             self._setup_colpar(f32)
         else:
             # one flat buffer for both gradients => a single all-reduce in the allreduce mode
@@ -194,6 +213,101 @@ class DeviceTrainer:
         self._tiny = torch.zeros(1, **f32)
 
     # ------------------------------------------------------------------------------------------
+    # rowshard set-up
+    # ------------------------------------------------------------------------------------------
+    def _setup_rowshard(self, model, f32, scalar_red):
+        """Split the (replicated, identically initialised) entity table into block-cyclic row shards.
+        Distributed: this rank keeps shard ``rank`` — table and gradient in torch symmetric memory so the
+        peers can read rows / add gradients through NVLink.  virtual_shards: all G shards local."""
+        full = model.entity_embedding.data
+        self.n_entity = full.shape[0]
+        if self.D % 4 != 0:
+            raise ValueError("rowshard needs hidden_dim % 4 == 0 (16-byte row segments)")
+        B, K = self.max_batch, self.K
+        if self.distributed:
+            import torch.distributed._symmetric_memory as symm
+
+            G, r = self.world, self.rank
+            group = self.group if self.group is not None else torch.distributed.group.WORLD
+            rows = ops.shard_rows(self.n_entity, G)
+            ptrs, self._symm = [], []
+            bufs = []
+            for _ in range(2):  # table shard, gradient shard
+                buf = symm.empty(rows, full.shape[1], dtype=torch.float32, device=self.dev)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, group)
+                p = [int(x) for x in hdl.buffer_ptrs]
+                if len(p) != G or p[r] != buf.data_ptr():
+                    raise RuntimeError("unexpected symmetric-memory pointer table")
+                bufs.append(buf)
+                ptrs.append(p)
+                self._symm.append(hdl)
+            mine = full[r::G]
+            bufs[0][: mine.shape[0]].copy_(mine)
+            self.ent_shards, self.g_shards = [bufs[0]], [bufs[1]]  # what this rank owns
+            self.shards = ops.ShardSet(ptrs[0], ptrs[1], scalar_red=scalar_red)
+            torch.cuda.synchronize(self.dev)
+            torch.distributed.barrier(group=self.group)
+        else:
+            G = self.virtual_shards or 1
+            self.ent_shards = ops.split_rows(full, G)
+            self.g_shards = [torch.zeros_like(t) for t in self.ent_shards]
+            self.shards = ops.ShardSet.of_tensors(self.ent_shards, self.g_shards, scalar_red=scalar_red)
+        self.n_shards = G
+        self.m_shards = [torch.zeros_like(t) for t in self.ent_shards]
+        self.v_shards = [torch.zeros_like(t) for t in self.ent_shards]
+        self.g_rel = torch.zeros_like(self.rel)
+        self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
+        self.neg = torch.empty((B, K), dtype=torch.int64, device=self.dev)
+        self.coef_pos = torch.empty(B, **f32)
+        self.coef_neg = torch.empty((B, K), **f32)
+        self._tiny = torch.zeros(1, **f32)
+
+    def sync_model(self):
+        """Write the trained shards back into ``model.entity_embedding`` (all-gather in the distributed
+        case) so evaluation / save / the user's own code see the current table."""
+        if self.mode != "rowshard":
+            return
+        full = self.model.entity_embedding.data
+        if self.distributed:
+            mine = self.ent_shards[0]
+            gathered = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=self.dev)
+            torch.distributed.all_gather_into_tensor(gathered, mine.contiguous(), group=self.group)
+            ops.merge_rows(list(gathered), self.n_entity, out=full)
+        else:
+            ops.merge_rows(self.ent_shards, self.n_entity, out=full)
+
+    def _step_rowshard(self, sample, weight, B, mode, h):
+        neg, coef_pos, coef_neg = self.neg[:B], self.coef_pos[:B], self.coef_neg[:B]
+        if h:
+            h[0].record()
+        ops.fused_forward_sharded_raw(self.spec, self.shards, self.n_entity, self.rel, sample, neg, weight, mode,
+                                      self.alpha, coef_pos, coef_neg, self.stats, self.ws)
+        if h:
+            h[1].record()
+        self.t += 1
+        if self.distributed:
+            parallel.allreduce_loss_sums(self.stats, self.group)
+        if h:
+            h[2].record()
+        ops.fused_backward_sharded_raw(self.spec, self.shards, self.n_entity, self.rel, sample, neg, mode, coef_pos,
+                                       coef_neg, self.stats, self.g_rel)
+        if h:
+            h[3].record()
+        if self.distributed:
+            # sums the replicated relation gradient AND marks "every rank's backward kernel has completed":
+            # all remote row-gradient REDs into my shard have landed before my Adam reads it
+            torch.distributed.all_reduce(self.g_rel, group=self.group)
+        b1, b2 = self.betas
+        for p, g, m, v in zip(self.ent_shards, self.g_shards, self.m_shards, self.v_shards):
+            ops.adam_step(p, g, m, v, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        if self.distributed:
+            # every owner has updated (and re-zeroed the gradient of) its shard before anyone's next step
+            torch.distributed.all_reduce(self._tiny, group=self.group)
+        return self.stats
+
+    # ------------------------------------------------------------------------------------------
     def _sample(self, sample, mode, neg):
         s = self.sampling
         if s.pool == "reference":  # the reference's host-drawn shared pool: 2K ids cross PCIe
@@ -215,6 +329,8 @@ class DeviceTrainer:
         coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
         self._sample(sample, mode, neg)
         h = self.hooks
+        if self.mode == "rowshard":
+            return self._step_rowshard(sample, weight, B, mode, h)
         if h:
             h[0].record()
         packed = self.packed_records

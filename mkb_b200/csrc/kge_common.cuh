@@ -119,6 +119,41 @@ __device__ __forceinline__ void red_add(float* p, const float (&v)[VEC]) {
   }
 }
 
+// Same reduction at system scope: the target row may live in a PEER GPU's HBM (row-sharded tables,
+// K7), where the add is performed by the owner's L2 over NVLink.  scalar != 0 issues four 4-byte REDs
+// instead of one 16-byte one (a debugging switch for fabrics that would not take the vector form).
+template <int VEC>
+__device__ __forceinline__ void red_add_sys(float* p, const float (&v)[VEC], int scalar) {
+  if constexpr (VEC == 4) {
+    if (!scalar) {
+      asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]),
+                   "f"(v[1]), "f"(v[2]), "f"(v[3])
+                   : "memory");
+      return;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k)
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p + k), "f"(v[k]) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Row-sharded entity table (K7).  Entity e lives on shard e % G at local row e / G (block-cyclic, so
+// hub entities spread evenly); every shard is reachable through a base pointer that is either local
+// HBM or a peer mapping over NVLink.  Ids are split ONCE into (shard, local row) and carried as
+// shard << 32 | row; the unsharded instantiations keep the plain id and compile to the same code as
+// before the sharded variants existed.
+// ----------------------------------------------------------------------------------------------
+template <bool SHARD>
+__device__ __forceinline__ int64_t shard_split(int64_t id, unsigned n_shards) {
+  if constexpr (SHARD) {
+    const unsigned u = (unsigned)id, q = u / n_shards;
+    return (int64_t)q | ((int64_t)(u - q * n_shards) << 32);
+  } else {
+    return id;
+  }
+}
+
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

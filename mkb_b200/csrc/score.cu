@@ -50,20 +50,34 @@ struct FwdParams {
   int ent_stride, rel_stride;
   int k_per_cta;
   float gamma, phase_div, alpha;
+  // K7 (row-sharded entity table): base pointer of every shard (local HBM or an NVLink peer mapping).
+  // Appended last so the unsharded kernels read their parameters at unchanged offsets.
+  const float* shard[KGE_MAX_SHARDS];
+  unsigned n_shards;
 };
+
+// Row of an entity from a split id (kge_common.cuh: shard_split): unsharded = id * stride.
+template <bool SHARD, typename P>
+__device__ __forceinline__ const float* ent_row(const P& p, int64_t sid) {
+  if constexpr (SHARD) {
+    return p.shard[(unsigned)(sid >> 32)] + (sid & 0xffffffffll) * (int64_t)p.ent_stride;
+  } else {
+    return p.ent + sid * (int64_t)p.ent_stride;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // positives only: one warp per triple (model(sample) and the 3-D sample path)
 // ------------------------------------------------------------------------------------------------
-template <int M, int VEC>
+template <int M, int VEC, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads) score_pos_kernel(FwdParams p) {
   using T = Traits<M>;
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (i >= p.B) return;
-  const float* h = p.ent + p.sample[3 * i + 0] * (int64_t)p.ent_stride;
+  const float* h = ent_row<SHARD>(p, shard_split<SHARD>(p.sample[3 * i + 0], p.n_shards));
   const float* r = p.rel + p.sample[3 * i + 1] * (int64_t)p.rel_stride;
-  const float* t = p.ent + p.sample[3 * i + 2] * (int64_t)p.ent_stride;
+  const float* t = ent_row<SHARD>(p, shard_split<SHARD>(p.sample[3 * i + 2], p.n_shards));
   float acc = 0.f;
   for (int d = lane * VEC; d < p.D; d += 32 * VEC) {
     float h0[VEC], h1[VEC] = {}, rr0[VEC], rr1[VEC] = {}, t0[VEC], t1[VEC] = {};
@@ -135,7 +149,7 @@ __device__ __forceinline__ void rows_reduce(const float* const (&row)[R], const 
 // ------------------------------------------------------------------------------------------------
 // forward with candidates: grid = (B, K-slices); FUSED => K-slices == 1 and the loss is folded in
 // ------------------------------------------------------------------------------------------------
-template <int M, bool HEAD, int VEC, bool FUSED>
+template <int M, bool HEAD, int VEC, bool FUSED, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];
@@ -145,8 +159,9 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t i = blockIdx.x;
-  const int64_t hid = p.sample[3 * i + 0], rid = p.sample[3 * i + 1], tidx = p.sample[3 * i + 2];
-  const float* fixed = p.ent + (HEAD ? tidx : hid) * (int64_t)p.ent_stride;
+  const int64_t hid = shard_split<SHARD>(p.sample[3 * i + 0], p.n_shards), rid = p.sample[3 * i + 1],
+                tidx = shard_split<SHARD>(p.sample[3 * i + 2], p.n_shards);
+  const float* fixed = ent_row<SHARD>(p, HEAD ? tidx : hid);
   const float* relrow = p.rel + rid * (int64_t)p.rel_stride;
   const bool want_pos = (FUSED || p.pos_score != nullptr) && blockIdx.y == 0;
 
@@ -168,8 +183,8 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
     if constexpr (T::NC == 2) st_shared<VEC>(q + p.Dp + d, q1);
     if (want_pos) {
       // positive = tail-batch formula on (h, r, t)   (compose/pipeline.py:211, mode=None)
-      const float* hrow = p.ent + hid * (int64_t)p.ent_stride;
-      const float* trow = p.ent + tidx * (int64_t)p.ent_stride;
+      const float* hrow = ent_row<SHARD>(p, hid);
+      const float* trow = ent_row<SHARD>(p, tidx);
       float t0[VEC], t1[VEC] = {};
       ld_global<VEC>(trow + d, t0);
       if constexpr (T::NC == 2) ld_global<VEC>(trow + p.D + d, t1);
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
   const int64_t* negrow = p.neg + i * (int64_t)p.K;
   for (int jb = j0 + warp; jb < j1; jb += kWarps * 32) {
     const int jmine = jb + lane * kWarps;
-    const int64_t my_id = jmine < j1 ? negrow[jmine] : 0;
+    const int64_t my_id = jmine < j1 ? shard_split<SHARD>(negrow[jmine], p.n_shards) : 0;
     const int cnt = min(32, (j1 - jb + kWarps - 1) / kWarps);
     constexpr int R = KGE_FWD_R, U = KGE_FWD_U;
     for (int m = 0; m < cnt; m += R) {
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
 #pragma unroll
       for (int r = 0; r < R; ++r) {  // rows past the end re-read the last valid one (result discarded)
         const int64_t id = __shfl_sync(kFull, my_id, min(m + r, cnt - 1));
-        rows[r] = p.ent + id * (int64_t)p.ent_stride;
+        rows[r] = ent_row<SHARD>(p, id);
       }
       float acc[R];
       rows_reduce<M, VEC, R, U>(rows, q, p.D, p.Dp, lane, acc);
@@ -272,11 +287,32 @@ struct BwdParams {
   int rec_B, n_rec;
   long long rec_stride;
   float phase_div;
+  // K7 (row-sharded entity table): table shards to read, gradient shards to add into (appended last)
+  const float* shard[KGE_MAX_SHARDS];
+  float* gshard[KGE_MAX_SHARDS];
+  unsigned n_shards;
+  int scalar_red;
 };
+
+// Gradient row of an entity from a split id: in the owner's (possibly remote) gradient shard.
+template <bool SHARD>
+__device__ __forceinline__ float* grad_row(const BwdParams& p, int64_t sid) {
+  if constexpr (SHARD) {
+    return p.gshard[(unsigned)(sid >> 32)] + (sid & 0xffffffffll) * (int64_t)p.g_ent_stride;
+  } else {
+    return p.grad_ent + sid * (int64_t)p.g_ent_stride;
+  }
+}
+// Entity-row gradient add: device scope locally, system scope when the row may be on a peer GPU.
+template <int VEC, bool SHARD>
+__device__ __forceinline__ void red_row(const BwdParams& p, float* dst, const float (&v)[VEC]) {
+  if constexpr (SHARD) red_add_sys<VEC>(dst, v, p.scalar_red);
+  else red_add<VEC>(dst, v);
+}
 
 constexpr int kTileK = 256;
 
-template <int M, bool HEAD, int VEC>
+template <int M, bool HEAD, int VEC, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC]
@@ -298,9 +334,10 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       p.neg ? reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(p.neg) + roff) + i * (int64_t)p.K : nullptr;
   const float* gnegrow =
       p.gneg ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.gneg) + roff) + i * (int64_t)p.K : nullptr;
-  const int64_t hid = smp[0], rid = smp[1], tidx = smp[2];
-  const float* hrow = p.ent + hid * (int64_t)p.ent_stride + p.col0;
-  const float* trow = p.ent + tidx * (int64_t)p.ent_stride + p.col0;
+  const int64_t hid = shard_split<SHARD>(smp[0], p.n_shards), rid = smp[1],
+                tidx = shard_split<SHARD>(smp[2], p.n_shards);
+  const float* hrow = ent_row<SHARD>(p, hid) + p.col0;
+  const float* trow = ent_row<SHARD>(p, tidx) + p.col0;
   const float* fixed = HEAD ? trow : hrow;
   const float* relrow = p.rel + rid * (int64_t)p.rel_stride + p.col0;
   float scale = 1.f;
@@ -341,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       const int n = min(kTileK, j1 - jt);
       __syncthreads();
       for (int k = tid; k < n; k += kThreads) {
-        s_idx[k] = negrow[jt + k];
+        s_idx[k] = shard_split<SHARD>(negrow[jt + k], p.n_shards);
         s_coef[k] = scale * gnegrow[jt + k];
       }
       __syncthreads();
@@ -353,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
           for (int u = 0; u < U; ++u) {
             const int k = jj + u * G;
             if (k < n) {
-              const float* row = p.ent + s_idx[k] * (int64_t)p.ent_stride + p.col0;
+              const float* row = ent_row<SHARD>(p, s_idx[k]) + p.col0;
               ld_global<VEC>(row + d, e0[u]);
               if constexpr (T::NC == 2) ld_global<VEC>(row + p.im_off + d, e1[u]);
             }
@@ -363,14 +400,14 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
             const int k = jj + u * G;
             if (k < n) {
               const float c = s_coef[k];
-              float* grow = p.grad_ent + s_idx[k] * (int64_t)p.g_ent_stride;
+              float* grow = grad_row<SHARD>(p, s_idx[k]);
               float g0[VEC], g1[VEC];
 #pragma unroll
               for (int v = 0; v < VEC; ++v)
                 cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
                             dq0[v], dq1[v]);
-              red_add<VEC>(grow + d, g0);
-              if constexpr (T::NC == 2) red_add<VEC>(grow + p.g_im_off + d, g1);
+              red_row<VEC, SHARD>(p, grow + d, g0);
+              if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
             }
           }
         }
@@ -457,16 +494,16 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
         }
         rel_bwd<M>(dr0, dr1, r0[v], r1[v], p.phase_div, gr0[v], gr1[v]);
       }
-      float* gh = p.grad_ent + hid * (int64_t)p.g_ent_stride;
-      float* gt = p.grad_ent + tidx * (int64_t)p.g_ent_stride;
+      float* gh = grad_row<SHARD>(p, hid);
+      float* gt = grad_row<SHARD>(p, tidx);
       float* gr = p.grad_rel + rid * (int64_t)p.g_rel_stride;
       if (!HEAD || do_pos) {
-        red_add<VEC>(gh + d, gh0);
-        if constexpr (T::NC == 2) red_add<VEC>(gh + p.g_im_off + d, gh1);
+        red_row<VEC, SHARD>(p, gh + d, gh0);
+        if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, gh + p.g_im_off + d, gh1);
       }
       if (HEAD || do_pos) {
-        red_add<VEC>(gt + d, gt0);
-        if constexpr (T::NC == 2) red_add<VEC>(gt + p.g_im_off + d, gt1);
+        red_row<VEC, SHARD>(p, gt + d, gt0);
+        if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, gt + p.g_im_off + d, gt1);
       }
       red_add<VEC>(gr + d, gr0);
       if constexpr (T::RC == 2) red_add<VEC>(gr + p.g_im_off + d, gr1);
@@ -508,9 +545,9 @@ static int set_smem(Kern kern, size_t bytes) {
   return KGE_OK;
 }
 
-template <int M, bool HEAD, int VEC, bool FUSED>
+template <int M, bool HEAD, int VEC, bool FUSED, bool SHARD = false>
 static int launch_neg(const FwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = score_neg_kernel<M, HEAD, VEC, FUSED>;
+  auto kern = score_neg_kernel<M, HEAD, VEC, FUSED, SHARD>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, st>>>(p);
@@ -538,7 +575,44 @@ static int dispatch_neg(int model, int mode, bool vec, const FwdParams& p, dim3 
   return KGE_E_MODEL;
 }
 
-static void fill_fwd(FwdParams& p, const kge_tables_t* t) {
+// K7: the sharded instantiations exist for the 16-byte vector path only
+template <bool FUSED>
+static int dispatch_neg_sharded(int model, int mode, const FwdParams& p, dim3 grid, size_t smem,
+                                cudaStream_t st) {
+#define KGE_CASE(MM)                                                                              \
+  case MM:                                                                                        \
+    return mode == KGE_HEAD_BATCH ? launch_neg<MM, true, 4, FUSED, true>(p, grid, smem, st)       \
+                                  : launch_neg<MM, false, 4, FUSED, true>(p, grid, smem, st);
+  switch (model) {
+    KGE_CASE(KGE_TRANSE)
+    KGE_CASE(KGE_DISTMULT)
+    KGE_CASE(KGE_COMPLEX)
+    KGE_CASE(KGE_ROTATE)
+  }
+#undef KGE_CASE
+  return KGE_E_MODEL;
+}
+
+// Argument checks shared by the sharded entry points; fills the kernel-side pointer tables.
+static int validate_sharded(const kge_tables_t* t, const kge_shards_t* sh, bool need_grad) {
+  if (!t || !t->relation || !sh) return KGE_E_NULL;
+  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (t->hidden_dim <= 0 || t->n_entity <= 0 || t->n_relation <= 0 || t->n_entity > INT32_MAX) return KGE_E_SIZE;
+  if (sh->n_shards < 1 || sh->n_shards > KGE_MAX_SHARDS) return KGE_E_SIZE;
+  if (t->hidden_dim % 4 != 0) return KGE_E_UNSUPPORTED;
+  if (!aligned16(t->relation)) return KGE_E_ALIGN;
+  for (int s = 0; s < sh->n_shards; ++s) {
+    if (!sh->entity[s] || (need_grad && !sh->grad_entity[s])) return KGE_E_NULL;
+    if (!aligned16(sh->entity[s]) || (need_grad && !aligned16(sh->grad_entity[s]))) return KGE_E_ALIGN;
+  }
+  return KGE_OK;
+}
+
+static void fill_fwd(FwdParams& p, const kge_tables_t* t, const kge_shards_t* sh = nullptr) {
+  if (sh) {
+    for (int s = 0; s < sh->n_shards; ++s) p.shard[s] = sh->entity[s];
+    p.n_shards = (unsigned)sh->n_shards;
+  }
   p.ent = t->entity;
   p.rel = t->relation;
   p.D = t->hidden_dim;
@@ -549,9 +623,9 @@ static void fill_fwd(FwdParams& p, const kge_tables_t* t) {
   p.phase_div = host_phase_div(t->embedding_range);
 }
 
-template <int M, bool HEAD, int VEC>
+template <int M, bool HEAD, int VEC, bool SHARD = false>
 static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = score_bwd_kernel<M, HEAD, VEC>;
+  auto kern = score_bwd_kernel<M, HEAD, VEC, SHARD>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, st>>>(p);
@@ -565,8 +639,17 @@ static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t s
 static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B, const int64_t* neg,
                    int64_t K, const float* gpos, const float* gneg, const float* stats,
                    const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st,
-                   int col0 = 0, int ncols = 0, int n_records = 1, long long record_stride = 0) {
+                   int col0 = 0, int ncols = 0, int n_records = 1, long long record_stride = 0,
+                   const kge_shards_t* sh = nullptr) {
   BwdParams p{};
+  if (sh) {  // K7: grad_ent is unused, rows resolve through the shard tables
+    for (int s = 0; s < sh->n_shards; ++s) {
+      p.shard[s] = sh->entity[s];
+      p.gshard[s] = sh->grad_entity[s];
+    }
+    p.n_shards = (unsigned)sh->n_shards;
+    p.scalar_red = sh->scalar_red;
+  }
   p.ent = t->entity;
   p.rel = t->relation;
   p.sample = sample;
@@ -597,7 +680,9 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.g_ent_stride = p.D * entity_comps(t->model);
   p.g_rel_stride = p.D * relation_comps(t->model);
   p.phase_div = host_phase_div(t->embedding_range);
-  const bool vec = can_vectorize(t, grad_ent, grad_rel) && (p.col0 % 4 == 0) && (p.D % 4 == 0);
+  const bool vec = sh ? aligned16(grad_rel)  // validate_sharded checked the rest
+                      : can_vectorize(t, grad_ent, grad_rel) && (p.col0 % 4 == 0) && (p.D % 4 == 0);
+  if (sh && !vec) return KGE_E_ALIGN;
   const int VEC = vec ? 4 : 1;
   const int chunks = (p.D + VEC - 1) / VEC;
   int tpg = 32;
@@ -622,6 +707,20 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
   dim3 grid((unsigned)total, (unsigned)ks);
   const size_t smem = (size_t)(G - 1) * entity_comps(t->model) * tpg * VEC * sizeof(float);
+  if (sh) {
+#define KGE_CASE(MM)                                                                  \
+  case MM:                                                                            \
+    return mode == KGE_HEAD_BATCH ? launch_bwd<MM, true, 4, true>(p, grid, smem, st)  \
+                                  : launch_bwd<MM, false, 4, true>(p, grid, smem, st);
+    switch (t->model) {
+      KGE_CASE(KGE_TRANSE)
+      KGE_CASE(KGE_DISTMULT)
+      KGE_CASE(KGE_COMPLEX)
+      KGE_CASE(KGE_ROTATE)
+    }
+#undef KGE_CASE
+    return KGE_E_MODEL;
+  }
 #define KGE_CASE(MM)                                                                       \
   case MM:                                                                                 \
     if (mode == KGE_HEAD_BATCH)                                                            \
@@ -767,4 +866,90 @@ extern "C" int kge_fused_bwd(const kge_tables_t* t, int mode, const int64_t* sam
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, grad_entity,
                  grad_relation, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: row-sharded entity table
+// ------------------------------------------------------------------------------------------------
+extern "C" int kge_score_fwd_sharded(const kge_tables_t* t, const kge_shards_t* sh, int mode,
+                                     const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                                     float* scores, kge_stream_t stream) {
+  int rc = validate_sharded(t, sh, false);
+  if (rc) return rc;
+  if (!sample || !scores) return KGE_E_NULL;
+  if (B < 0 || B > INT32_MAX || (neg && (K <= 0 || K > INT32_MAX))) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  if (B == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdParams p{};
+  fill_fwd(p, t, sh);
+  p.sample = sample;
+  p.B = (int)B;
+  if (!neg) {
+    p.pos_score = scores;
+    p.K = 0;
+    const unsigned grid = (unsigned)((B + kWarps - 1) / kWarps);
+    switch (t->model) {
+      case KGE_TRANSE: score_pos_kernel<KGE_TRANSE, 4, true><<<grid, kThreads, 0, st>>>(p); break;
+      case KGE_DISTMULT: score_pos_kernel<KGE_DISTMULT, 4, true><<<grid, kThreads, 0, st>>>(p); break;
+      case KGE_COMPLEX: score_pos_kernel<KGE_COMPLEX, 4, true><<<grid, kThreads, 0, st>>>(p); break;
+      case KGE_ROTATE: score_pos_kernel<KGE_ROTATE, 4, true><<<grid, kThreads, 0, st>>>(p); break;
+    }
+    KGE_LAUNCH_CHECK();
+    return KGE_OK;
+  }
+  p.neg = neg;
+  p.neg_score = scores;
+  p.K = (int)K;
+  const int want = (4 * sm_count() + (int)B - 1) / (int)B;
+  const int maxks = (p.K + 63) / 64;
+  int ks = want < 1 ? 1 : (want > maxks ? maxks : want);
+  p.k_per_cta = (p.K + ks - 1) / ks;
+  ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
+  const size_t smem = (size_t)entity_comps(t->model) * p.Dp * sizeof(float);
+  return dispatch_neg_sharded<false>(t->model, mode, p, dim3((unsigned)B, (unsigned)ks), smem, st);
+}
+
+extern "C" int kge_fused_fwd_sharded(const kge_tables_t* t, const kge_shards_t* sh, int mode,
+                                     const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                                     const float* weight, float alpha, float* pos_score, float* neg_score,
+                                     float* coef_pos, float* coef_neg, float* stats, void* workspace,
+                                     kge_stream_t stream) {
+  int rc = validate_sharded(t, sh, false);
+  if (rc) return rc;
+  if (!sample || !neg || !weight || !coef_pos || !coef_neg || !stats || !workspace) return KGE_E_NULL;
+  if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  FwdParams p{};
+  fill_fwd(p, t, sh);
+  p.sample = sample;
+  p.neg = neg;
+  p.weight = weight;
+  p.pos_score = pos_score;
+  p.neg_score = neg_score;
+  p.coef_pos = coef_pos;
+  p.coef_neg = coef_neg;
+  p.stats = stats;
+  p.ticket = reinterpret_cast<unsigned int*>(workspace);
+  p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 16);
+  p.B = (int)B;
+  p.K = (int)K;
+  p.k_per_cta = (int)K;
+  p.alpha = alpha;
+  const size_t smem = ((size_t)entity_comps(t->model) * p.Dp + (size_t)K) * sizeof(float);
+  if (smem > 200 * 1024) return KGE_E_UNSUPPORTED;
+  return dispatch_neg_sharded<true>(t->model, mode, p, dim3((unsigned)B, 1), smem, (cudaStream_t)stream);
+}
+
+extern "C" int kge_fused_bwd_sharded(const kge_tables_t* t, const kge_shards_t* sh, int mode,
+                                     const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                                     const float* coef_pos, const float* coef_neg, const float* stats,
+                                     const float* grad_loss, float* grad_relation, kge_stream_t stream) {
+  int rc = validate_sharded(t, sh, true);
+  if (rc) return rc;
+  if (!sample || !neg || !coef_pos || !coef_neg || !stats || !grad_relation) return KGE_E_NULL;
+  if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX) return KGE_E_SIZE;
+  if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
+  return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, nullptr, grad_relation,
+                 (cudaStream_t)stream, 0, 0, 1, 0, sh);
 }

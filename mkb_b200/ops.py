@@ -37,6 +37,19 @@ class TableSpec:
         return N.KgeTables(ent.data_ptr(), rel.data_ptr(), ent.shape[0], rel.shape[0], self.hidden_dim,
                            self.model_id, self.gamma, self.embedding_range)
 
+    def struct_sharded(self, n_entity, rel):
+        """Tables struct of a row-sharded model: no local entity table, the GLOBAL entity count."""
+        rc = 2 if self.model_name == "ComplEx" else 1
+        if rel.shape[1] != rc * self.hidden_dim:
+            raise ValueError(f"{self.model_name}: relation table {tuple(rel.shape)} does not match "
+                             f"hidden_dim={self.hidden_dim}")
+        return N.KgeTables(None, rel.data_ptr(), int(n_entity), rel.shape[0], self.hidden_dim, self.model_id,
+                           self.gamma, self.embedding_range)
+
+    @property
+    def entity_dim(self):
+        return self.hidden_dim * (2 if self.model_name in ("ComplEx", "RotatE") else 1)
+
 
 def _mode_id(mode):
     if mode == "head-batch":
@@ -297,6 +310,119 @@ def adam_slice_bcast(replica_ptrs, self_index, grad_slice, m_slice, v_slice, row
                                      beta1, beta2, eps, int(bool(zero_grad)), N.stream_ptr(device)),
             "kge_adam_slice_bcast")
     N.count_launch()
+
+
+# ---------------------------------------------------------------------------------------------
+# K7: row-sharded entity table (block-cyclic: entity e -> shard e % G, local row e / G)
+# ---------------------------------------------------------------------------------------------
+def shard_rows(n_entity, n_shards, shard=None):
+    """Rows of shard ``shard`` (or, with ``shard=None``, of the largest shard = the common allocation)."""
+    if shard is None:
+        return -(-n_entity // n_shards)
+    return (n_entity - shard + n_shards - 1) // n_shards if shard < n_entity else 0
+
+
+def split_rows(table, n_shards):
+    """Full [N, dim] table -> list of G [ceil(N/G), dim] shards (zero-padded), block-cyclic."""
+    rows = shard_rows(table.shape[0], n_shards)
+    out = []
+    for s in range(n_shards):
+        sh = torch.zeros((rows, table.shape[1]), dtype=table.dtype, device=table.device)
+        part = table[s::n_shards]
+        sh[: part.shape[0]] = part
+        out.append(sh)
+    return out
+
+
+def merge_rows(shards, n_entity, out=None):
+    """Inverse of split_rows."""
+    G = len(shards)
+    if out is None:
+        out = torch.empty((n_entity, shards[0].shape[1]), dtype=shards[0].dtype, device=shards[0].device)
+    for s, sh in enumerate(shards):
+        out[s::G] = sh[: shard_rows(n_entity, G, s)]
+    return out
+
+
+class ShardSet:
+    """Base pointers of every shard of the entity table (and of its gradient) as seen from THIS GPU:
+    local tensors' data_ptr() for shards held here, NVLink peer mappings for the others."""
+
+    def __init__(self, entity_ptrs, grad_ptrs=None, scalar_red=False):
+        G = len(entity_ptrs)
+        if not 1 <= G <= N.MAX_SHARDS:
+            raise ValueError(f"1..{N.MAX_SHARDS} shards supported, got {G}")
+        if grad_ptrs is not None and len(grad_ptrs) != G:
+            raise ValueError("entity_ptrs and grad_ptrs differ in length")
+        self.n_shards = G
+        st = N.KgeShards()
+        for s in range(G):
+            st.entity[s] = int(entity_ptrs[s])
+            st.grad_entity[s] = int(grad_ptrs[s]) if grad_ptrs is not None else None
+        st.n_shards = G
+        st.scalar_red = int(bool(scalar_red))
+        self._struct = st
+
+    @classmethod
+    def of_tensors(cls, shards, grads=None, **kw):
+        """All shards local (one GPU holding every shard: tests, single-GPU runs of the sharded path)."""
+        for t in list(shards) + list(grads or []):
+            N.require_cuda(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("shards must be contiguous float32 CUDA tensors")
+        obj = cls([t.data_ptr() for t in shards], [t.data_ptr() for t in grads] if grads is not None else None, **kw)
+        obj._keep = (list(shards), list(grads or []))
+        return obj
+
+    def struct(self):
+        return self._struct
+
+
+def fused_forward_sharded_raw(spec, shards, n_entity, rel, sample, neg, weight, mode, alpha, coef_pos, coef_neg,
+                              stats, ws, pos_score=None, neg_score=None):
+    """K2 through the shard table (kge_fused_fwd_sharded) into caller-owned buffers."""
+    lib = N.load()
+    tb = spec.struct_sharded(n_entity, rel)
+    B, K = neg.shape
+    N.check(lib.kge_fused_fwd_sharded(C.byref(tb), C.byref(shards.struct()), _mode_id(mode), N.ptr(sample), B,
+                                      N.ptr(neg), K, N.ptr(weight), alpha, N.ptr(pos_score), N.ptr(neg_score),
+                                      N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats), N.ptr(ws),
+                                      N.stream_ptr(rel.device)), "kge_fused_fwd_sharded")
+    N.count_launch()
+
+
+def fused_backward_sharded_raw(spec, shards, n_entity, rel, sample, neg, mode, coef_pos, coef_neg, stats, g_rel,
+                               grad_loss=None):
+    """K3 through the shard table: entity-row gradients are ADDED into the owners' gradient shards
+    (system-scope REDs, possibly over NVLink), the relation gradient into the local ``g_rel``."""
+    lib = N.load()
+    tb = spec.struct_sharded(n_entity, rel)
+    B, K = neg.shape
+    N.check(lib.kge_fused_bwd_sharded(C.byref(tb), C.byref(shards.struct()), _mode_id(mode), N.ptr(sample), B,
+                                      N.ptr(neg), K, N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats),
+                                      N.ptr(grad_loss), N.ptr(g_rel), N.stream_ptr(rel.device)),
+            "kge_fused_bwd_sharded")
+    N.count_launch()
+
+
+def score_sharded(spec, shards, n_entity, rel, sample, neg=None, mode=None):
+    """``model(sample[, negative_sample, mode])`` of a row-sharded model (no autograd): float32
+    ``[B,1]`` / ``[B,K]``."""
+    lib = N.load()
+    N.require_cuda(rel, sample, neg)
+    rel = rel.detach().contiguous()
+    sample = _prep_ids(sample, rel.device)
+    neg = _prep_ids(neg, rel.device)
+    B = sample.shape[0]
+    K = 1 if neg is None else neg.shape[1]
+    out = torch.empty((B, K), dtype=torch.float32, device=rel.device)
+    tb = spec.struct_sharded(n_entity, rel)
+    with torch.cuda.device(rel.device):
+        N.check(lib.kge_score_fwd_sharded(C.byref(tb), C.byref(shards.struct()), _mode_id(mode if neg is not None else None),
+                                          N.ptr(sample), B, N.ptr(neg), 0 if neg is None else K, N.ptr(out),
+                                          N.stream_ptr(rel.device)), "kge_score_fwd_sharded")
+    N.count_launch()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -150,3 +150,32 @@ def test_shuffled_batches_match_the_reference_loader(num_workers):
         for i, d in enumerate(batches):
             np.testing.assert_array_equal(d["sample"].numpy(), g[f"nw{num_workers}/epoch{epoch}/b{i}"])
             assert d["mode"] == str(g[f"nw{num_workers}/epoch{epoch}/m{i}"])
+
+
+def test_shard_helpers_round_trip_and_layout():
+    """K7 host logic: block-cyclic split/merge, shard sizes, struct layout, argument validation."""
+    from mkb_b200 import ops
+
+    assert ctypes.sizeof(_native.KgeShards) == 2 * 8 * _native.MAX_SHARDS + 8
+    assert _native.KgeShards.n_shards.offset == 2 * 8 * _native.MAX_SHARDS
+    full = torch.arange(11 * 3, dtype=torch.float32).view(11, 3)
+    for G in (1, 2, 3, 4, 16):
+        shards = ops.split_rows(full, G)
+        assert len(shards) == G and all(s.shape == (ops.shard_rows(11, G), 3) for s in shards)
+        assert sum(ops.shard_rows(11, G, s) for s in range(G)) == 11
+        for e in range(11):  # entity e lives on shard e % G at local row e // G
+            assert torch.equal(shards[e % G][e // G], full[e])
+        assert torch.equal(ops.merge_rows(shards, 11), full)
+    lib = _native.load()
+    t = _native.KgeTables(None, None, 10, 2, 4, 0, 1.0, 0.5)
+    sh = _native.KgeShards()
+    sh.n_shards = 2
+    assert lib.kge_score_fwd_sharded(ctypes.byref(t), ctypes.byref(sh), 0, None, 1, None, 0, None, None) == -1
+    t.relation = 256  # never dereferenced: the checks below fail first
+    assert lib.kge_score_fwd_sharded(ctypes.byref(t), ctypes.byref(sh), 0, None, 1, None, 0, None, None) == -1  # shard ptr NULL
+    sh.n_shards = 17
+    assert lib.kge_score_fwd_sharded(ctypes.byref(t), ctypes.byref(sh), 0, None, 1, None, 0, None, None) == -2
+    sh.n_shards = 2
+    t.hidden_dim = 6
+    assert lib.kge_fused_bwd_sharded(ctypes.byref(t), ctypes.byref(sh), 0, None, 1, None, 1, None, None, None, None,
+                                     None, None) == -6
