@@ -1,0 +1,216 @@
+"""TEST INFRASTRUCTURE: build tests/emu/_build/libkge_emu.so — the kernels of mkb_b200/csrc compiled
+for the HOST against the CUDA execution-model emulation in tests/emu/include/cuda_runtime.h.
+
+The product sources are not modified: this script rewrites, on the fly, the three constructs g++
+cannot parse
+
+  * ``kernel<<<grid, block, smem, stream>>>(args)``  ->  ``emu::launch(grid, block, smem, stream, [&]{ kernel(args); })``
+  * ``extern __shared__ [__align__(n)] T name[];``   ->  ``T* name = (T*)emu::S.dyn_smem;``
+  * the inline-PTX statements (red.*.add[.v4].f32, sqrt/rsqrt.approx) -> plain C++
+
+and compiles everything except rank_tc.cu (tcgen05/TMA PTX cannot be emulated; kge_rank_all then
+falls back to the fp32 tile kernel, which is what the emulation tests cover).
+"""
+import os
+import re
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "mkb_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libkge_emu.so")
+SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu"]
+HEADERS = ["kge_common.cuh"]
+
+
+def _balanced(text, start, open_ch="(", close_ch=")"):
+    """Index just past the bracket that closes the one at text[start]."""
+    assert text[start] == open_ch, text[start:start + 20]
+    depth, i, in_str = 0, start, False
+    while i < len(text):
+        c = text[i]
+        if in_str:
+            if c == "\\":
+                i += 1
+            elif c == '"':
+                in_str = False
+        elif c == '"':
+            in_str = True
+        elif c == open_ch:
+            depth += 1
+        elif c == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+    raise ValueError("unbalanced brackets")
+
+
+def rewrite_launches(text):
+    out, pos = [], 0
+    while True:
+        k = text.find("<<<", pos)
+        if k < 0:
+            out.append(text[pos:])
+            return "".join(out)
+        # kernel expression: identifier, optionally followed by a <template, argument, list>
+        j = k
+        while j > pos and text[j - 1].isspace():
+            j -= 1
+        if text[j - 1] == ">":
+            depth, j = 0, j - 1
+            while True:
+                if text[j] == ">":
+                    depth += 1
+                elif text[j] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j -= 1
+        while j > pos and (text[j - 1].isalnum() or text[j - 1] in "_:"):
+            j -= 1
+        kernel = text[j:k].strip()
+        e = text.find(">>>", k)
+        cfg = text[k + 3:e]
+        a0 = e + 3
+        while text[a0].isspace():
+            a0 += 1
+        a1 = _balanced(text, a0)
+        args = text[a0 + 1:a1 - 1]
+        parts = [c.strip() for c in _split_top(cfg)]
+        while len(parts) < 4:
+            parts.append("0")
+        out.append(text[pos:j])
+        out.append(f"emu::launch({parts[0]}, {parts[1]}, (size_t)({parts[2]}), (cudaStream_t)({parts[3]}), "
+                   f"[&]() {{ {kernel}({args}); }})")
+        pos = a1
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, []
+    for c in s:
+        if c in "(<[":
+            depth += 1
+        elif c in ")>]":
+            depth -= 1
+        if c == "," and depth == 0:
+            parts.append("".join(cur))
+            cur = []
+        else:
+            cur.append(c)
+    parts.append("".join(cur))
+    return parts
+
+
+def rewrite_extern_shared(text):
+    return re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];",
+                  r"\1* \2 = reinterpret_cast<\1*>(emu::S.dyn_smem);", text)
+
+
+def rewrite_asm(text):
+    out, pos = [], 0
+    for m in re.finditer(r"\basm\s*(?:volatile\s*)?\(", text):
+        if m.start() < pos:
+            continue
+        end = _balanced(text, m.end() - 1)
+        body = text[m.end():end - 1]
+        semi = text.index(";", end)
+        lit = re.match(r'\s*"((?:[^"\\]|\\.)*)"', body)
+        ptx, rest = lit.group(1), body[lit.end():]
+        ops, i = [], 0
+        while True:  # operands: "constraint"(expression) with balanced parentheses
+            mm = re.compile(r'"(=?[a-z]+)"\s*\(').search(rest, i)
+            if not mm:
+                break
+            if mm.group(1) == "memory":
+                i = mm.end()
+                continue
+            j = _balanced(rest, mm.end() - 1)
+            ops.append((mm.group(1), rest[mm.end():j - 1]))
+            i = j
+        outs = [e for c, e in ops if c.startswith("=")]
+        ins = [e for c, e in ops if not c.startswith("=")]
+        if re.match(r"red\.relaxed\.(gpu|sys)\.global\.add\.v4\.f32", ptx):
+            p, v = ins[0], ins[1:5]
+            code = "{ float* _p = (float*)(" + p + "); " + " ".join(f"_p[{i}] += ({e});" for i, e in enumerate(v)) + " }"
+        elif re.match(r"red\.relaxed\.(gpu|sys)\.global\.add\.f32", ptx):
+            code = f"{{ *(float*)({ins[0]}) += ({ins[1]}); }}"
+        elif ptx.startswith("sqrt.approx"):
+            code = f"{outs[0]} = sqrtf({ins[0]});"
+        elif ptx.startswith("rsqrt.approx"):
+            code = f"{outs[0]} = 1.0f / sqrtf({ins[0]});"
+        else:
+            raise ValueError(f"no emulation for PTX statement: {ptx}")
+        out.append(text[pos:m.start()])
+        out.append(code)
+        pos = semi + 1
+    out.append(text[pos:])
+    return "".join(out)
+
+
+def preprocess(name):
+    text = open(os.path.join(CSRC, name)).read()
+    text = text.replace('#include "../../include/kge_b200.h"', f'#include "{os.path.join(ROOT, "include", "kge_b200.h")}"')
+    text = rewrite_asm(rewrite_extern_shared(rewrite_launches(text)))
+    return f"// GENERATED by tests/emu/build_emu.py from mkb_b200/csrc/{name} — do not edit\n" + text
+
+
+STUB = """// rank_tc.cu (tcgen05 / TMA) is not emulated: report "unsupported" so kge_rank_all uses the tile kernel
+#include "kge_common.cuh"
+namespace kge {
+int rank_tc_launch(const float*, const float*, int64_t, int, const int64_t*, int, const kge_filter_csr_t*, bool,
+                   const float*, const int64_t*, unsigned long long*, float*, bool, cudaStream_t) {
+  return KGE_E_UNSUPPORTED;
+}
+}  // namespace kge
+extern "C" long kge_emu_launch_count(void) { return emu::S.launches; }
+"""
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps += [os.path.join(ROOT, "include", "kge_b200.h"), os.path.join(HERE, "include", "cuda_runtime.h"), __file__]
+    return any(os.path.getmtime(f) > t for f in deps)
+
+
+def build(force=False):
+    if not force and not stale():
+        return LIB
+    shutil.rmtree(OUT, ignore_errors=True)
+    os.makedirs(OUT)
+    for h in HEADERS:
+        open(os.path.join(OUT, h), "w").write(preprocess(h))
+    cpps = []
+    for s in SOURCES:
+        dst = os.path.join(OUT, s[:-3] + ".cpp")
+        open(dst, "w").write(preprocess(s))
+        cpps.append(dst)
+    stub = os.path.join(OUT, "rank_tc_stub.cpp")
+    open(stub, "w").write(STUB)
+    cpps.append(stub)
+    flags = ["-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+             "-I", os.path.join(HERE, "include"), "-I", OUT]
+    procs = []
+    for c in cpps:
+        o = c[:-4] + ".o"
+        procs.append((c, o, subprocess.Popen(["g++", *flags, "-c", c, "-o", o], stdout=subprocess.PIPE,
+                                             stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for c, o, p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"g++ failed on {c}:\n{log[-4000:]}")
+        objs.append(o)
+    subprocess.run(["g++", "-shared", "-o", LIB, *objs], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,285 @@
+"""The CUDA kernels' LOGIC on a CPU emulation of the CUDA execution model (tests/emu): the sources of
+mkb_b200/csrc are compiled for the host — fibers for threads, rendezvous for __syncthreads and warp
+shuffles, host memory for global memory — and called through the same C ABI with numpy buffers.
+
+This container has no GPU; these tests are how a kernel change is checked against the oracle before it
+ever reaches a B200 (indexing, tiling, reductions, loss algebra, atomic scatter, sharded addressing,
+Philox streams, rank counting).  They are NOT a CPU path of the product (the package refuses to run
+without the real CUDA library) and say nothing about performance.  rank_tc.cu (tcgen05/TMA) cannot be
+emulated and is covered by the GPU tests only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, MODES, score_tol
+from emu import harness as H
+from oracle import kge_oracle as ko
+
+
+def _problem(model, Nn, R, D, B, K, seed, gamma=9.0):
+    rng = np.random.RandomState(seed)
+    ent, rel = ko.init_tables(model, Nn, R, D, gamma, seed=seed)
+    ent *= 2.5
+    sample = np.stack([rng.randint(Nn, size=B), rng.randint(R, size=B), rng.randint(Nn, size=B)], 1).astype(np.int64)
+    neg = rng.randint(Nn, size=(B, K)).astype(np.int64)
+    w = rng.uniform(0.1, 0.5, size=B).astype(np.float32)
+    return ent, rel, sample, neg, w
+
+
+def _close(a, ref, rel=1e-4):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    bad = np.abs(a - ref) > score_tol(ref, rel)
+    assert not bad.any(), f"{bad.sum()} / {bad.size} outside tol; max abs err {np.abs(a - ref).max():.3e}"
+
+
+def _grad_close(a, ref, rel=1e-4):
+    err = np.abs(np.asarray(a, np.float64) - ref).max()
+    assert err <= rel * max(np.abs(ref).max(), 1e-30), f"grad max err {err:.3e} vs scale {np.abs(ref).max():.3e}"
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("D,B,K", [(16, 5, 19), (5, 3, 7), (132, 2, 40)])
+def test_fused_step_vs_oracle(model, mode, D, B, K):
+    Nn, R, gamma = 60, 4, 9.0
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=D + B)
+    loss, pos, ngs, ge, gr = ko.train_step(model, ent, rel, sample, neg, mode, w, gamma=gamma)
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    _close(f["pos"], pos)
+    _close(f["neg"], ngs)
+    assert abs(f["stats"][3] - loss) <= 1e-5 * abs(loss)
+    _close(H.score(model, ent, rel, gamma, sample), pos)
+    _close(H.score(model, ent, rel, gamma, sample, neg, mode), ngs)
+    g_ent, g_rel = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f)
+    _grad_close(g_ent, ge)
+    _grad_close(g_rel, gr)
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("G", (1, 2, 3, 16))
+def test_sharded_kernels_equal_unsharded(model, mode, G):
+    """K7: the forward through the shard table is BIT-identical to the unsharded kernel, the backward
+    lands every row gradient in the owner's shard (ragged shards: 43 % G != 0)."""
+    Nn, R, D, B, K, gamma = 43, 4, 16, 6, 21, 9.0
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=3 * G)
+    f0 = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    ge0, gr0 = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f0)
+    shards = H.split_rows(ent, G)
+    grads = [np.zeros_like(s) for s in shards]
+    st = H.shards_struct(shards, grads)
+    f1 = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, shards=st)
+    for k in f0:
+        assert np.array_equal(f0[k], f1[k]), k
+    assert np.array_equal(H.score(model, ent, rel, gamma, sample, shards=st), f0["pos"])
+    assert np.array_equal(H.score(model, ent, rel, gamma, sample, neg, mode, shards=st), f0["neg"])
+    _, gr1 = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f1, shards=st)
+    ge1 = H.merge_rows(grads, Nn)
+    _grad_close(ge1, ge0.astype(np.float64), rel=1e-6)
+    _grad_close(gr1, gr0.astype(np.float64), rel=1e-6)
+    for s, g in enumerate(grads):  # padding rows of ragged shards stay untouched
+        assert not g[(Nn - s + G - 1) // G:].any()
+    # scalar-RED debugging switch gives the same gradient
+    grads2 = [np.zeros_like(s) for s in shards]
+    st2 = H.shards_struct(shards, grads2, scalar_red=True)
+    H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f1, shards=st2)
+    _grad_close(H.merge_rows(grads2, Nn), ge1.astype(np.float64), rel=1e-6)
+
+
+def test_unfused_loss_and_score_backward_vs_oracle():
+    """kge_adv_loss_fwd/bwd + kge_score_bwd (the generic three-call route) == the oracle."""
+    l = H.lib()
+    rng = np.random.RandomState(5)
+    B, K = 9, 70
+    pos = rng.normal(0, 3, size=(B, 1)).astype(np.float32)
+    neg = rng.normal(0, 3, size=(B, K)).astype(np.float32)
+    w = rng.uniform(0.1, 0.5, B).astype(np.float32)
+    stats = np.zeros(4, np.float32)
+    ws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, np.uint8)
+    H.ok(l.kge_adv_loss_fwd(H.P(pos), H.P(neg), H.P(w), B, K, 0.7, H.P(stats), H.P(ws), None))
+    ref = ko.adversarial_loss(pos, neg, w, 0.7)
+    assert abs(stats[3] - ref) <= 1e-6 * abs(ref)
+    gp, gn = np.empty(B, np.float32), np.empty((B, K), np.float32)
+    H.ok(l.kge_adv_loss_bwd(H.P(pos), H.P(neg), H.P(w), B, K, 0.7, H.P(stats), None, H.P(gp), H.P(gn), None))
+    rp, rn = ko.adversarial_loss_grads(pos, neg, w, 0.7)
+    _grad_close(gp, rp.reshape(-1), 1e-5)
+    _grad_close(gn, rn, 1e-5)
+    for model in MODELS:
+        for mode in MODES:
+            ent, rel, sample, ngs, _ = _problem(model, 40, 3, 12, B, 17, seed=9)
+            gsc = rng.normal(size=(B, 17)).astype(np.float32)
+            ge, gr = np.zeros_like(ent), np.zeros_like(rel)
+            tb = H.tables(model, ent, rel, 9.0)
+            H.ok(l.kge_score_bwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(ngs), 17, H.P(gsc), H.P(ge),
+                                 H.P(gr), None))
+            re_, rr_ = ko.score_grads(model, ent, rel, sample, ngs, mode, gsc, gamma=9.0)
+            _grad_close(ge, re_)
+            _grad_close(gr, rr_)
+            gpos = rng.normal(size=(B, 1)).astype(np.float32)
+            ge, gr = np.zeros_like(ent), np.zeros_like(rel)
+            H.ok(l.kge_score_bwd(C.byref(tb), 0, H.P(sample), B, None, 0, H.P(gpos), H.P(ge), H.P(gr), None))
+            re_, rr_ = ko.score_grads(model, ent, rel, sample, None, None, gpos, gamma=9.0)
+            _grad_close(ge, re_)
+            _grad_close(gr, rr_)
+
+
+@pytest.mark.parametrize("model", ("RotatE", "DistMult"))
+def test_chunked_and_multi_record_backward(model):
+    """kge_fused_bwd_chunk over column chunks == kge_fused_bwd; n_records > 1 == per-record launches."""
+    l = H.lib()
+    Nn, R, D, B, K, gamma, mode = 50, 3, 64, 5, 12, 9.0, "head-batch"
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=1)
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    ge, gr = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f)
+    nc, rc = H.NC[model], H.RC[model]
+    tb = H.tables(model, ent, rel, gamma)
+    for col, wd in ((0, 32), (32, 16), (48, 16)):
+        gec, grc = np.zeros((Nn, nc * wd), np.float32), np.zeros((R, rc * wd), np.float32)
+        H.ok(l.kge_fused_bwd_chunk(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(f["cpos"]),
+                                   H.P(f["cneg"]), H.P(f["stats"]), None, col, wd, 1, 0, H.P(gec), H.P(grc), None))
+        _grad_close(gec, ge.reshape(Nn, nc, D)[:, :, col:col + wd].reshape(Nn, nc * wd).astype(np.float64), 1e-6)
+        _grad_close(grc, gr.reshape(R, rc, D)[:, :, col:col + wd].reshape(R, rc * wd).astype(np.float64), 1e-6)
+    # packed records: [sample | neg | cpos | cneg | stats] per record
+    G = 3
+    o_neg, o_cp = B * 24, B * 24 + B * K * 8
+    o_cn = o_cp + B * 4
+    o_st = (o_cn + B * K * 4 + 15) // 16 * 16
+    rec = o_st + 16
+    buf = np.zeros(G * rec, np.uint8)
+    parts = []
+    for r in range(G):
+        _, _, s_r, n_r, w_r = _problem(model, Nn, R, D, B, K, seed=20 + r)
+        f_r = H.fused_fwd(model, ent, rel, gamma, s_r, n_r, w_r, mode)
+        base = buf[r * rec:(r + 1) * rec]
+        base[:o_neg] = s_r.view(np.uint8).reshape(-1)
+        base[o_neg:o_cp] = n_r.view(np.uint8).reshape(-1)
+        base[o_cp:o_cn] = f_r["cpos"].view(np.uint8)
+        base[o_cn:o_cn + B * K * 4] = f_r["cneg"].view(np.uint8).reshape(-1)
+        base[o_st:o_st + 16] = f_r["stats"].view(np.uint8)
+        parts.append((s_r, n_r, f_r))
+    col, wd = 16, 32
+    g1, r1 = np.zeros((Nn, nc * wd), np.float32), np.zeros((R, rc * wd), np.float32)
+    p0 = buf.ctypes.data
+    H.ok(l.kge_fused_bwd_chunk(C.byref(tb), H.mode_id(mode), p0, B, p0 + o_neg, K, p0 + o_cp, p0 + o_cn, p0 + o_st, None,
+                               col, wd, G, rec, H.P(g1), H.P(r1), None))
+    total = np.sum([f_r["stats"] for *_, f_r in parts], axis=0).astype(np.float32)
+    g2, r2 = np.zeros_like(g1), np.zeros_like(r1)
+    for s_r, n_r, f_r in parts:
+        H.ok(l.kge_fused_bwd_chunk(C.byref(tb), H.mode_id(mode), H.P(s_r), B, H.P(n_r), K, H.P(f_r["cpos"]),
+                                   H.P(f_r["cneg"]), H.P(total), None, col, wd, 1, 0, H.P(g2), H.P(r2), None))
+    assert np.abs(g2).max() > 0
+    _grad_close(g1, g2.astype(np.float64), 1e-6)
+    _grad_close(r1, r2.astype(np.float64), 1e-6)
+
+
+def test_adam_variants_vs_oracle():
+    l = H.lib()
+    rng = np.random.RandomState(0)
+    rows, comps, D = 7, 2, 24
+    p = rng.normal(size=(rows, comps * D)).astype(np.float32)
+    g = rng.normal(size=p.shape).astype(np.float32)
+    m, v = np.abs(rng.normal(size=p.shape)).astype(np.float32) * 0.1, np.abs(rng.normal(size=p.shape)).astype(np.float32) * 0.01
+    rp, rm, rv = ko.adam_step(p.astype(np.float64), g.astype(np.float64), m.astype(np.float64), v.astype(np.float64), 3, lr=1e-3)
+    p1, g1, m1, v1 = p.copy(), g.copy(), m.copy(), v.copy()
+    H.ok(l.kge_adam_step(H.P(p1), H.P(g1), H.P(m1), H.P(v1), p1.size, 3, 1e-3, 0.9, 0.999, 1e-8, 1, None))
+    np.testing.assert_allclose(p1, rp, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(m1, rm, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(v1, rv, rtol=2e-6, atol=1e-7)
+    assert not g1.any()  # zero_grad folded in
+    # column chunks (table layout for param/moments, dense chunk gradient)
+    p2, m2, v2 = p.copy(), m.copy(), v.copy()
+    for col, wd in ((0, 8), (8, 16)):
+        gc = np.ascontiguousarray(g.reshape(rows, comps, D)[:, :, col:col + wd].reshape(rows, comps * wd))
+        H.ok(l.kge_adam_step_chunk(H.P(p2), H.P(gc), H.P(m2), H.P(v2), rows, comps, wd, col, comps * D, D, 3, 1e-3, 0.9,
+                                   0.999, 1e-8, 1, None))
+        assert not gc.any()
+    assert np.array_equal(p2, p1) and np.array_equal(m2, m1) and np.array_equal(v2, v1)
+    # slice + broadcast into 3 replicas (dense slice moments)
+    reps = [p.copy() for _ in range(3)]
+    arr = (C.c_void_p * 3)(*[r.ctypes.data for r in reps])
+    for col, wd in ((0, 8), (8, 16)):
+        sl = lambda x: np.ascontiguousarray(x.reshape(rows, comps, D)[:, :, col:col + wd].reshape(rows, comps * wd))
+        gs, ms, vs = sl(g), sl(m), sl(v)
+        H.ok(l.kge_adam_slice_bcast(arr, 3, 1, H.P(gs), H.P(ms), H.P(vs), rows, comps, wd, col, comps * D, D, 3, 1e-3,
+                                    0.9, 0.999, 1e-8, 1, None))
+        assert np.array_equal(ms, sl(m1)) and np.array_equal(vs, sl(v1))
+    for r in reps:
+        assert np.array_equal(r, p1)
+
+
+def test_samplers_bit_exact(sampler_cases):
+    """kge_sample_negatives == the oracle's Philox specification, kge_filter_pool == the reference's
+    own draws (golden vectors), incl. the status word."""
+    l = H.lib()
+    g = sampler_cases
+    triples = [tuple(int(x) for x in r) for r in g["triples"]]
+    Nn = int(g["N"])
+    hc, tc = ko.build_filter_csr(triples, Nn, "head"), ko.build_filter_csr(triples, Nn, "tail")
+    for call, mode in enumerate(("head-batch", "tail-batch", "tail-batch")):
+        sample = np.ascontiguousarray(g[f"gen{call}/sample"], dtype=np.int64)
+        fs = H.csr_struct(hc if mode == "head-batch" else tc)
+        for sort_rows in (1, 0):
+            out = np.full((sample.shape[0], 16), -1, np.int64)
+            status = np.zeros(1, np.int32)
+            H.ok(l.kge_sample_negatives(C.byref(fs), H.mode_id(mode), H.P(sample), sample.shape[0], 16, Nn, 42, call,
+                                        sort_rows, H.P(out), H.P(status), None))
+            ref, st = ko.sample_negatives_independent(42, call, sample, mode, Nn, hc, tc, 16, sort_rows=bool(sort_rows))
+            assert status[0] == st == 0
+            np.testing.assert_array_equal(out, ref)
+    rng = np.random.RandomState(42)
+    for step in range(6):
+        sample = np.ascontiguousarray(g[f"gen{step}/sample"], dtype=np.int64)
+        mode = str(g[f"gen{step}/mode"])
+        size = g[f"gen{step}/neg"].shape[1]
+        pool = rng.randint(Nn, size=2 * size).astype(np.int64)
+        fs = H.csr_struct(hc if mode == "head-batch" else tc)
+        out = np.full((sample.shape[0], size), -1, np.int64)
+        status = np.zeros(1, np.int32)
+        H.ok(l.kge_filter_pool(C.byref(fs), H.mode_id(mode), H.P(sample), sample.shape[0], size, Nn, H.P(pool),
+                               pool.shape[0], H.P(out), H.P(status), None))
+        assert status[0] == 0
+        np.testing.assert_array_equal(out, g[f"gen{step}/neg"])
+    # a key that is not in the graph sets bit 0 (the reference raises KeyError)
+    missing = None
+    keys = set(int(k) for k in hc[0])
+    for r in range(int(g["R"])):
+        for t in range(Nn):
+            if r * Nn + t not in keys:
+                missing = np.array([[0, r, t]], np.int64)
+                break
+        if missing is not None:
+            break
+    if missing is not None:
+        fs = H.csr_struct(hc)
+        out, status = np.zeros((1, 4), np.int64), np.zeros(1, np.int32)
+        H.ok(l.kge_sample_negatives(C.byref(fs), 1, H.P(missing), 1, 4, Nn, 1, 0, 1, H.P(out), H.P(status), None))
+        assert status[0] & 1
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_rank_tile_kernel_vs_reference(eval_cases, model):
+    """kge_rank_all (fp32 tile kernel; the tcgen05 variant is GPU-only) == the reference's ranks."""
+    l = H.lib()
+    g = eval_cases
+    Nn = 50
+    allt = [tuple(int(x) for x in r) for part in ("train", "valid", "test") for r in g[part]]
+    gamma = float(g[f"{model}/gamma"])
+    ent = np.ascontiguousarray(g[f"{model}/ent"], np.float32)
+    rel = np.ascontiguousarray(g[f"{model}/rel"], np.float32)
+    hc, tc = ko.build_filter_csr(allt, Nn, "head"), ko.build_filter_csr(allt, Nn, "tail")
+    test = np.ascontiguousarray(g["test"], np.int64)
+    tb = H.tables(model, ent, rel, gamma)
+    for mode in MODES:
+        fs = H.csr_struct(hc if mode == "head-batch" else tc)
+        Q = test.shape[0]
+        ranks = np.zeros(Q, np.int64)
+        scores = np.full((Q, Nn), np.nan, np.float32)
+        ws = np.zeros(l.kge_rank_workspace_bytes(C.byref(tb), Q) + 64, np.uint8)
+        H.ok(l.kge_rank_all(C.byref(tb), H.mode_id(mode), H.P(test), Q, C.byref(fs), H.P(ranks), H.P(scores), H.P(ws), None))
+        ref = g[f"{model}/{mode}/ranks"]
+        _, contested = ko.rank_all(model, ent, rel, test, mode, hc, tc, gamma=gamma, tie_margin=1e-5)
+        assert np.all(np.abs(ranks - ref) <= contested), (ranks, ref)
+        assert (ranks == ref).mean() >= 0.95
+        _close(scores, g[f"{model}/{mode}/scores"])
