@@ -101,6 +101,20 @@ int kge_adv_loss_bwd(const float* pos_score, const float* neg_score, const float
                      float* grad_pos, float* grad_neg, kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * KL divergence between row softmaxes, the distillation loss.  Replaces losses.KlDivergence.__call__
+ * (mkb/losses/kl_divergence.py:22-29):
+ *   loss[0] = mean_{i,j} q_ij (log q_ij - log p_ij),  p = softmax(student / T, dim=1),
+ *                                                      q = softmax(teacher / T, dim=1)
+ * student, teacher: [B,K] row-major.  workspace: kge_loss_workspace_bytes(B) bytes, zero-filled once.
+ * Backward: grad_student[B,K] = dL/dstudent; grad_teacher (may be NULL) = dL/dteacher; grad_loss is
+ * a device scalar or NULL (= 1).
+ * ------------------------------------------------------------------------------------------- */
+int kge_kl_div_fwd(const float* student, const float* teacher, int64_t B, int64_t K, float T, float* loss,
+                   void* workspace, kge_stream_t stream);
+int kge_kl_div_bwd(const float* student, const float* teacher, int64_t B, int64_t K, float T,
+                   const float* grad_loss, float* grad_student, float* grad_teacher, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  fused gather -> score(1+K) -> adversarial loss, ONE kernel.  Replaces the three calls at
  *     mkb/compose/pipeline.py:211, :230-232, :234 (model(sample); model(sample, neg, mode); loss).
  * Outputs: pos_score[B] and neg_score[B,K] (either may be NULL = not wanted), stats[4] as above,
@@ -228,6 +242,18 @@ size_t kge_rank_workspace_bytes(const kge_tables_t* tables, int64_t Q);
 int kge_rank_all(const kge_tables_t* tables, int mode, const int64_t* queries, int64_t Q,
                  const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out, void* workspace,
                  kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8  exact top-k of every row of a score matrix.  Replaces the argsort-then-slice of
+ *     utils.TopK._get_rank (mkb/utils/top_k.py:226-234) and of the distillation loop's top-k negative
+ *     sampling (mkb/distillation/top_k_sampling.py:664-677).
+ * scores: [rows, cols] with row stride row_stride (floats).  indices[rows,k] receives the columns of
+ * the k largest scores of each row in DESCENDING score order, equal scores by ascending column (the
+ * order of a stable descending argsort); values[rows,k] (optional) the scores themselves.
+ * 1 <= k <= min(cols, 1024) (KGE_E_SIZE / KGE_E_UNSUPPORTED otherwise).  No workspace.
+ * ------------------------------------------------------------------------------------------- */
+int kge_topk_rows(const float* scores, int64_t rows, int64_t cols, int64_t row_stride, int32_t k,
+                  int64_t* indices, float* values, kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense Adam step over one table (the user-owned torch.optim.Adam of README.md:123-126 called at

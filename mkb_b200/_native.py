@@ -65,6 +65,9 @@ PROTOTYPES = {
     "kge_loss_workspace_bytes": (C.c_size_t, [_I64]),
     "kge_adv_loss_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, C.c_float, _P, _P, _P]),
     "kge_adv_loss_bwd": (C.c_int, [_P, _P, _P, _I64, _I64, C.c_float, _P, _P, _P, _P, _P]),
+    "kge_kl_div_fwd": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _P]),
+    "kge_kl_div_bwd": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _P, _P]),
+    "kge_topk_rows": (C.c_int, [_P, _I64, _I64, _I64, C.c_int32, _P, _P, _P]),
     "kge_fused_fwd": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, C.c_float,
                                 _P, _P, _P, _P, _P, _P, _P]),
     "kge_fused_bwd": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, _P, _P, _P,

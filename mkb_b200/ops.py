@@ -13,7 +13,8 @@ from . import _native as N
 
 __all__ = [
     "score", "adversarial_loss", "fused_adversarial_step", "sample_negatives", "filter_pool",
-    "rank_all", "adam_step", "FilterCSR", "TableSpec",
+    "rank_all", "adam_step", "FilterCSR", "TableSpec", "kl_divergence", "topk_rows", "ShardSet", "shard_rows",
+    "split_rows", "merge_rows", "score_sharded",
 ]
 
 
@@ -186,6 +187,75 @@ def adversarial_loss(pos, neg, weight, alpha=0.5):
     """losses.Adversarial.__call__ (mkb/losses/adversarial.py:21-30) as one kernel."""
     N.require_cuda(pos, neg, weight)
     return _AdvLossFn.apply(pos, neg, weight, float(alpha))
+
+
+# ---------------------------------------------------------------------------------------------
+# KL divergence between row softmaxes (distillation loss) + autograd
+# ---------------------------------------------------------------------------------------------
+class _KlDivFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, T):
+        lib = N.load()
+        s = student.contiguous().float()
+        t = teacher.contiguous().float()
+        if s.dim() != 2 or s.shape != t.shape:
+            raise ValueError("student_score and teacher_score must both be [n, k]")
+        B, K = s.shape
+        loss = torch.empty(1, dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            ws = _loss_workspace(B, s.device)
+            N.check(lib.kge_kl_div_fwd(N.ptr(s), N.ptr(t), B, K, T, N.ptr(loss), N.ptr(ws), N.stream_ptr(s.device)),
+                    "kge_kl_div_fwd")
+        N.count_launch()
+        ctx.save_for_backward(s, t)
+        ctx.T = T
+        ctx.shapes = (student.shape, teacher.shape)
+        return loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        s, t = ctx.saved_tensors
+        lib = N.load()
+        B, K = s.shape
+        gs = torch.empty_like(s)
+        gt = torch.empty_like(t) if ctx.needs_input_grad[1] else None
+        gl = grad_loss.contiguous().float()
+        with torch.cuda.device(s.device):
+            N.check(lib.kge_kl_div_bwd(N.ptr(s), N.ptr(t), B, K, ctx.T, N.ptr(gl), N.ptr(gs), N.ptr(gt),
+                                       N.stream_ptr(s.device)), "kge_kl_div_bwd")
+        N.count_launch()
+        return gs.view(ctx.shapes[0]), (gt.view(ctx.shapes[1]) if gt is not None else None), None
+
+
+def kl_divergence(student_score, teacher_score, T=1):
+    """losses.KlDivergence.__call__ (mkb/losses/kl_divergence.py:22-29) as one kernel each way."""
+    N.require_cuda(student_score, teacher_score)
+    return _KlDivFn.apply(student_score, teacher_score, float(T))
+
+
+# ---------------------------------------------------------------------------------------------
+# K8: exact row-wise top-k
+# ---------------------------------------------------------------------------------------------
+def topk_rows(scores, k, return_values=False):
+    """Columns of the ``k`` largest entries of every row of ``scores[rows, cols]`` in descending score
+    order, ties by ascending column (= ``argsort(descending, stable)[:, :k]``) -> int64 ``[rows, k]``."""
+    lib = N.load()
+    N.require_cuda(scores)
+    if scores.dim() == 1:
+        scores = scores.view(1, -1)
+    if scores.dim() != 2:
+        raise ValueError("scores must be [rows, cols]")
+    x = scores.detach()
+    if x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.float().contiguous()
+    rows, cols = x.shape
+    idx = torch.empty((rows, k), dtype=torch.int64, device=x.device)
+    val = torch.empty((rows, k), dtype=torch.float32, device=x.device) if return_values else None
+    with torch.cuda.device(x.device):
+        N.check(lib.kge_topk_rows(N.ptr(x), rows, cols, x.stride(0) if rows > 1 else cols, int(k), N.ptr(idx),
+                                  N.ptr(val), N.stream_ptr(x.device)), "kge_topk_rows")
+    N.count_launch()
+    return (idx, val) if return_values else idx
 
 
 # ---------------------------------------------------------------------------------------------

@@ -286,6 +286,16 @@ inline T atomicOr(T* p, T v) {
   *p = old | v;
   return old;
 }
+inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline float __fadd_rn(float a, float b) { return a + b; }

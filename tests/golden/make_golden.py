@@ -273,6 +273,119 @@ def gen_eval_cases():
     print("eval_cases", len(out))
 
 
+def _typed_graph():
+    """40 entities, 4 relations with the four mapping categories (r0 one-to-one, r1 one-to-many,
+    r2 many-to-one, r3 many-to-many) and a few (head, tail) pairs connected by several relations, so
+    that types_relations / detail_eval / TestDatasetRelation's bias all have something to do."""
+    rng = np.random.RandomState(12)
+    t = set()
+    perm = rng.permutation(40)
+    for i in range(0, 36, 2):  # r0: disjoint pairs -> 1 head per tail, 1 tail per head
+        t.add((int(perm[i]), 0, int(perm[i + 1])))
+    for h in (0, 1, 2, 3):  # r1: 4 heads x 6 tails each, tails disjoint -> 1_M
+        for k in range(6):
+            t.add((h, 1, 4 + 6 * h + k))
+    for tl in (30, 31, 32):  # r2: many heads per tail, one tail per head -> M_1
+        for k in range(7):
+            t.add((7 * (tl - 30) + k, 2, tl))
+    for _ in range(70):  # r3: many-to-many
+        t.add((int(rng.randint(12)), 3, int(rng.randint(12, 24))))
+    t = sorted(t)
+    extra = [(h, 3, tl) for h, r, tl in t if r == 1][:6] + [(h, 1, tl) for h, r, tl in t if r == 2][:3]
+    t = sorted(set(t) | set(extra))
+    order = rng.permutation(len(t))
+    t = [t[i] for i in order]
+    n_test = 24
+    return t[n_test + 10:], t[n_test:n_test + 10], t[:n_test]
+
+
+def gen_next_rows():
+    """TestDatasetRelation items, eval_relations, types_relations / detail_eval,
+    utils.TopK, utils.make_prediction, pRotatE forward/backward (incl. the trainable modulus),
+    KlDivergence value and gradient."""
+    from mkb import utils
+    from mkb.models import pRotatE
+
+    out = {}
+    N, R = 40, 4
+    train, valid, test = _typed_graph()
+    entities = {f"e{i}": i for i in range(N)}
+    relations = {f"r{i}": i for i in range(R)}
+    true_triples = train + valid + test
+    out["train"], out["valid"], out["test"] = (np.array(x, dtype=np.int64) for x in (train, valid, test))
+    tdr = ref_base.TestDatasetRelation(triples=test, true_triples=true_triples, entities=entities, relations=relations)
+    items = [tdr[i] for i in range(len(test))]
+    out["rel/cand"] = np.stack([_np(c) for _, c, _, _ in items])
+    out["rel/bias"] = np.stack([_np(b) for _, _, b, _ in items])
+    for name, gamma in MODEL_GAMMA.items():
+        torch.manual_seed(77)
+        model = getattr(models, name)(hidden_dim=8, entities=entities, relations=relations, gamma=gamma)
+        with torch.no_grad():
+            model.entity_embedding.mul_(4.0)
+            model.relation_embedding.mul_(4.0)
+        out[f"{name}/ent"], out[f"{name}/rel"] = _np(model.entity_embedding), _np(model.relation_embedding)
+        out[f"{name}/gamma"] = np.float64(gamma)
+        ev = evaluation.Evaluation(entities=entities, relations=relations, batch_size=4, true_triples=true_triples,
+                                   num_workers=0)
+        m = ev.eval_relations(model=model, dataset=test)
+        out[f"{name}/rel_metrics"] = np.array([m[f"{k}_relations"] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")])
+        types = ev.types_relations(model=model, dataset=test)
+        out[f"{name}/types"] = np.array([types[f"r{i}"] for i in range(R)])
+        frame = ev.detail_eval(model=model, dataset=test)
+        out[f"{name}/detail"] = frame.to_numpy(dtype=np.float64)
+        out[f"{name}/detail_cols"] = np.array(["|".join(c) for c in frame.columns])
+        out[f"{name}/detail_index"] = np.array(list(frame.index))
+        topk = utils.TopK(entities=entities, relations=relations)
+        out[f"{name}/top_heads"] = np.array([entities[e] for e in topk.top_heads(k=7, model=model, relation="r1", tail="e3")])
+        out[f"{name}/top_tails"] = np.array([entities[e] for e in topk.top_tails(k=7, model=model, head="e5", relation=2)])
+        out[f"{name}/top_relations"] = np.array([relations[r] for r in topk.top_relations(k=2, model=model, head=4, tail="e9")])
+        out[f"{name}/prediction"] = _np(utils.make_prediction(model=model, dataset=test[:9], batch_size=4, num_workers=0,
+                                                              device="cpu"))
+    # pRotatE: forward / loss / autograd gradients (fp32 and fp64), both modes, vector and scalar dims
+    for D in (8, 5):
+        for mode in ("tail-batch", "head-batch"):
+            torch.manual_seed(11 + D)
+            model = pRotatE(hidden_dim=D, entities=entities, relations=relations, gamma=9.0)
+            with torch.no_grad():
+                model.entity_embedding.mul_(3.0)
+                model.relation_embedding.mul_(3.0)
+            r2 = np.random.RandomState(D)
+            sample = torch.tensor(np.stack([r2.randint(N, size=6), r2.randint(R, size=6), r2.randint(N, size=6)], 1))
+            neg = torch.tensor(r2.randint(N, size=(6, 7)))
+            weight = torch.tensor(r2.uniform(0.1, 0.5, 6).astype(np.float32))
+            key = f"pRotatE_D{D}_{mode}"
+            out[f"{key}/ent"], out[f"{key}/rel"] = _np(model.entity_embedding).copy(), _np(model.relation_embedding).copy()
+            out[f"{key}/modulus"] = _np(model.modulus).copy()
+            out[f"{key}/sample"], out[f"{key}/neg"], out[f"{key}/weight"] = _np(sample), _np(neg), _np(weight)
+            for tag, mdl in (("f32", model), ("f64", __import__("copy").deepcopy(model).double())):
+                w = weight.double() if tag == "f64" else weight
+                mdl.zero_grad()
+                pos = mdl(sample)
+                ns = mdl(sample, neg, mode)
+                loss = losses.Adversarial(alpha=0.5)(pos, ns, w)
+                loss.backward()
+                out[f"{key}/{tag}/pos"], out[f"{key}/{tag}/neg_score"] = _np(pos), _np(ns)
+                out[f"{key}/{tag}/loss"] = np.float64(loss.item())
+                out[f"{key}/{tag}/grad_ent"] = _np(mdl.entity_embedding.grad)
+                out[f"{key}/{tag}/grad_rel"] = _np(mdl.relation_embedding.grad)
+                out[f"{key}/{tag}/grad_modulus"] = _np(mdl.modulus.grad)
+                out[f"{key}/{tag}/score3d"] = _np(mdl(torch.stack([sample[:4], sample[2:6]])))
+    # KlDivergence (losses/kl_divergence.py:22-29): value and gradient w.r.t. the student scores
+    r3 = np.random.RandomState(9)
+    for T in (1, 3):
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            student = torch.tensor(r3.normal(0, 2, size=(5, 11)), dtype=dt, requires_grad=True)
+            teacher = torch.tensor(r3.normal(0, 2, size=(5, 11)), dtype=dt)
+            loss = losses.KlDivergence()(student, teacher, T=T)
+            loss.backward()
+            out[f"kl_T{T}/{tag}/student"], out[f"kl_T{T}/{tag}/teacher"] = _np(student), _np(teacher)
+            out[f"kl_T{T}/{tag}/loss"] = np.float64(loss.item())
+            out[f"kl_T{T}/{tag}/grad"] = _np(student.grad)
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **out)
+    print("next_rows", len(out))
+
+
+
 def gen_eval_doctest():
     """evaluation/evaluation.py:39-116 — train RotatE(dim 3) for 5 epochs on a 4-triple toy graph
     with the doctest's own loop (note: it never calls zero_grad, so .grad accumulates), then pin
@@ -352,7 +465,9 @@ def gen_loader_order():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader"]
+    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next"]
+    if "next" in which:
+        gen_next_rows()
     if "loader" in which:
         gen_loader_order()
     if "step" in which:

@@ -283,3 +283,62 @@ def test_rank_tile_kernel_vs_reference(eval_cases, model):
         assert np.all(np.abs(ranks - ref) <= contested), (ranks, ref)
         assert (ranks == ref).mean() >= 0.95
         _close(scores, g[f"{model}/{mode}/scores"])
+
+
+@pytest.fixture(scope="module")
+def next_rows():
+    from conftest import load_golden
+
+    return load_golden("next_rows.npz")
+
+
+def test_kl_divergence_vs_reference(next_rows):
+    """kge_kl_div_fwd/bwd == the reference's KlDivergence (value and autograd gradient), T = 1 and 3."""
+    l = H.lib()
+    g = next_rows
+    for T in (1, 3):
+        s = np.ascontiguousarray(g[f"kl_T{T}/f32/student"], np.float32)
+        t = np.ascontiguousarray(g[f"kl_T{T}/f32/teacher"], np.float32)
+        B, K = s.shape
+        loss = np.zeros(1, np.float32)
+        ws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, np.uint8)
+        H.ok(l.kge_kl_div_fwd(H.P(s), H.P(t), B, K, float(T), H.P(loss), H.P(ws), None))
+        ref = float(g[f"kl_T{T}/f32/loss"])
+        assert abs(loss[0] - ref) <= 1e-5 * abs(ref)
+        gs, gt = np.empty_like(s), np.empty_like(t)
+        H.ok(l.kge_kl_div_bwd(H.P(s), H.P(t), B, K, float(T), None, H.P(gs), H.P(gt), None))
+        _grad_close(gs, g[f"kl_T{T}/f32/grad"].astype(np.float64), 1e-4)
+        # teacher gradient and fp64 value: closed forms
+        s64, t64 = s.astype(np.float64) / T, t.astype(np.float64) / T
+        lp = s64 - s64.max(1, keepdims=True)
+        lp -= np.log(np.exp(lp).sum(1, keepdims=True))
+        lq = t64 - t64.max(1, keepdims=True)
+        lq -= np.log(np.exp(lq).sum(1, keepdims=True))
+        q = np.exp(lq)
+        kl = (q * (lq - lp)).sum(1, keepdims=True)
+        assert abs(loss[0] - kl.sum() / (B * K)) <= 1e-5 * abs(ref)
+        _grad_close(gt, q * ((lq - lp) - kl) / (B * K * T), 1e-4)
+        _grad_close(gs, (np.exp(lp) - q) / (B * K * T), 1e-4)
+
+
+@pytest.mark.parametrize("cols,k", [(1, 1), (7, 7), (50, 1), (300, 5), (1000, 64), (4099, 1000), (2500, 1024)])
+def test_topk_rows_matches_stable_argsort(cols, k):
+    """kge_topk_rows: descending scores, ties by ascending column, incl. heavy ties, +-0, infinities."""
+    l = H.lib()
+    rng = np.random.RandomState(cols + k)
+    rows = 4
+    x = rng.normal(size=(rows, cols + 3)).astype(np.float32)  # row stride > cols
+    x[1] = np.round(x[1])  # many exact ties
+    x[2, ::3] = 0.0
+    x[2, 1::3] = -0.0
+    if cols > 3:
+        x[3, 0], x[3, 1], x[3, 2] = np.inf, -np.inf, np.inf
+    idx = np.full((rows, k), -1, np.int64)
+    val = np.full((rows, k), np.nan, np.float32)
+    H.ok(l.kge_topk_rows(H.P(x), rows, cols, cols + 3, k, H.P(idx), H.P(val), None))
+    for r in range(rows):
+        ref = np.argsort(-x[r, :cols].astype(np.float64), kind="stable")[:k]
+        np.testing.assert_array_equal(idx[r], ref)
+        np.testing.assert_array_equal(val[r], x[r, ref])
+    assert l.kge_topk_rows(H.P(x), rows, cols, cols + 3, cols + 1, H.P(idx), None, None) == -2
+    assert l.kge_topk_rows(H.P(x), rows, 5000, 5000, 1025, H.P(idx), None, None) == -6

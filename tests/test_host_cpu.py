@@ -179,3 +179,122 @@ def test_shard_helpers_round_trip_and_layout():
     t.hidden_dim = 6
     assert lib.kge_fused_bwd_sharded(ctypes.byref(t), ctypes.byref(sh), 0, None, 1, None, 1, None, None, None, None,
                                      None, None) == -6
+
+
+# --------------------------------------------------------------------------------------------------
+# evaluation host logic driven by an oracle-backed stand-in model: everything
+# around the kernels — TestDataset / TestDatasetRelation items, the stream API, the position count
+# that replaces argsort, relation categories, the detail_eval frame — checked against fixtures made by
+# executing the reference.  The stand-in only replaces the CUDA scoring calls.
+# --------------------------------------------------------------------------------------------------
+class _OracleModel:
+    def __init__(self, name, ent, rel, gamma):
+        self.name, self.ent, self.rel, self.gamma = name, ent, rel, gamma
+        self.entity_embedding = torch.zeros(1)
+        self.training = True
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self):
+        self.training = True
+        return self
+
+    def __call__(self, sample, negative_sample=None, mode=None):
+        s = sample.numpy()
+        if s.ndim == 3:
+            flat = ko.score(self.name, self.ent, self.rel, s.reshape(-1, 3), gamma=self.gamma)
+            return torch.from_numpy(flat.reshape(s.shape[0], s.shape[1]).astype(np.float32))
+        neg = None if negative_sample is None else negative_sample.numpy()
+        return torch.from_numpy(ko.score(self.name, self.ent, self.rel, s, neg, mode, gamma=self.gamma).astype(np.float32))
+
+
+@pytest.fixture(scope="module")
+def next_rows():
+    from conftest import load_golden
+
+    return load_golden("next_rows.npz")
+
+
+def _next_setup(g, name):
+    from mkb_b200 import evaluation
+
+    entities = {f"e{i}": i for i in range(40)}
+    relations = {f"r{i}": i for i in range(4)}
+    true = [tuple(int(x) for x in r) for part in ("train", "valid", "test") for r in g[part]]
+    test = [tuple(int(x) for x in r) for r in g["test"]]
+    ev = evaluation.Evaluation(entities=entities, relations=relations, batch_size=4, true_triples=true)
+    m = _OracleModel(name, g[f"{name}/ent"].astype(np.float64), g[f"{name}/rel"].astype(np.float64), float(g[f"{name}/gamma"]))
+    return ev, m, test, true, entities, relations
+
+
+def test_test_datasets_match_reference_items(eval_cases, next_rows):
+    g = eval_cases
+    true = [tuple(int(x) for x in r) for part in ("train", "valid", "test") for r in g[part]]
+    test = [tuple(int(x) for x in r) for r in g["test"]]
+    ents, rels = {f"e{i}": i for i in range(50)}, {f"r{i}": i for i in range(3)}
+    for mode in ("head-batch", "tail-batch"):
+        td = datasets.TestDataset(triples=test, true_triples=true, entities=ents, relations=rels, mode=mode)
+        assert len(td) == len(test)
+        items = [td[i] for i in range(len(test))]
+        np.testing.assert_array_equal(np.stack([c.numpy() for _, c, _, _ in items]), g[f"{mode}/cand"])
+        np.testing.assert_array_equal(np.stack([b.numpy() for _, _, b, _ in items]), g[f"{mode}/bias"])
+        batch = td.collate_fn(items[:3])
+        assert batch["sample"].shape == (3, 3) and batch["negative_sample"].shape == (3, 50) and batch["mode"] == mode
+        assert batch["filter_bias"].dtype == torch.float32 and batch["negative_sample"].dtype == torch.int64
+    g = next_rows
+    ev, _, test, true, ents, rels = _next_setup(g, "RotatE")
+    tdr = datasets.TestDatasetRelation(triples=test, true_triples=true, entities=ents, relations=rels)
+    items = [tdr[i] for i in range(len(test))]
+    np.testing.assert_array_equal(np.stack([c.numpy() for _, c, _, _ in items]), g["rel/cand"])
+    np.testing.assert_array_equal(np.stack([b.numpy() for _, _, b, _ in items]), g["rel/bias"])
+    assert items[0][3] == "relation-batch" and (g["rel/bias"] != 0).sum() > 0
+    stream = ev.get_relation_stream(test)
+    assert len(stream) == -(-len(test) // 4) and sum(b["sample"].shape[0] for b in stream) == len(test)
+
+
+@pytest.mark.parametrize("name", ("TransE", "DistMult", "ComplEx", "RotatE"))
+def test_stream_api_and_relation_metrics_match_reference(next_rows, name):
+    from mkb_b200.evaluation.evaluation import _Mean
+
+    g = next_rows
+    ev, m, test, *_ = _next_setup(g, name)
+    keys = ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")
+    got = ev.eval_relations(model=m, dataset=test)
+    np.testing.assert_allclose([got[f"{k}_relations"] for k in keys], g[f"{name}/rel_metrics"], atol=1e-4)
+    metrics = ev.compute_score(model=m, test_set=ev.get_relation_stream(test), metrics={k: _Mean() for k in keys},
+                               device="cpu")
+    np.testing.assert_allclose([round(metrics[k].get(), 4) for k in keys], g[f"{name}/rel_metrics"], atol=1e-4)
+    assert m.training
+
+
+@pytest.mark.parametrize("name", ("TransE", "RotatE"))
+def test_types_relations_and_detail_frame_match_reference(next_rows, name, monkeypatch):
+    g = next_rows
+    ev, m, test, true, *_ = _next_setup(g, name)
+    types = ev.types_relations(model=m, dataset=test)
+    assert [types[f"r{i}"] for i in range(4)] == list(g[f"{name}/types"])
+    hc, tc = ko.build_filter_csr(true, 40, "head"), ko.build_filter_csr(true, 40, "tail")
+
+    def oracle_ranks(model, dataset, mode):
+        r, _ = ko.rank_all(name, m.ent, m.rel, np.asarray(dataset, dtype=np.int64), mode, hc, tc, gamma=m.gamma)
+        return torch.from_numpy(np.asarray(r, dtype=np.int64))
+
+    monkeypatch.setattr(ev, "ranks", oracle_ranks)
+    frame = ev.detail_eval(model=m, dataset=test)
+    assert ["|".join(c) for c in frame.columns] == list(g[f"{name}/detail_cols"])
+    assert list(frame.index) == list(g[f"{name}/detail_index"])
+    np.testing.assert_allclose(frame.to_numpy(dtype=np.float64), g[f"{name}/detail"], atol=1e-4)
+    # the reference's own driver for the same table
+    from mkb_b200.evaluation.evaluation import _TYPES, _new_metrics
+
+    by_id = {int(k[1:]): v for k, v in types.items()}
+    metrics = {mode: {t: _new_metrics() for t in _TYPES} for mode in ("head-batch", "tail-batch")}
+    for stream in ev.get_entity_stream(test):
+        metrics = ev.compute_detailled_score(model=m, test_set=stream, metrics=metrics, types_relations=by_id,
+                                             device="cpu")
+    import pandas as pd
+
+    frame2 = ev._detail_frame(pd, metrics, by_id)
+    np.testing.assert_allclose(frame2.to_numpy(dtype=np.float64), g[f"{name}/detail"], atol=1e-4)
