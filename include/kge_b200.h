@@ -27,12 +27,12 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 
 typedef void* kge_stream_t; /* cudaStream_t */
 
-/* mkb/models/{transe,distmult,complex,rotate}.py */
-enum kge_model { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_ROTATE = 3 };
+/* mkb/models/{transe,distmult,complex,rotate,protate}.py */
+enum kge_model { KGE_TRANSE = 0, KGE_DISTMULT = 1, KGE_COMPLEX = 2, KGE_ROTATE = 3, KGE_PROTATE = 4 };
 /* `mode` of BaseModel.batch (mkb/models/base.py:153-164); mode=None uses the tail-batch formula */
 enum kge_mode { KGE_TAIL_BATCH = 0, KGE_HEAD_BATCH = 1 };
 
@@ -58,6 +58,10 @@ typedef struct kge_tables {
   int32_t model; /* enum kge_model */
   float gamma;
   float embedding_range;
+  /* pRotatE only (mkb/models/protate.py:72,91): DEVICE pointer to the trainable scalar `modulus`
+   * (score = gamma - modulus * sum |sin(phase)|); read on the device so a training step never waits
+   * for the host.  NULL for the other models. */
+  const float* modulus;
 } kge_tables_t;
 
 int kge_abi_version(void);
@@ -154,6 +158,17 @@ int kge_fused_bwd_chunk(const kge_tables_t* tables, int mode, const int64_t* sam
                         const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,
                         int32_t n_records, int64_t record_stride_bytes, float* grad_entity_chunk,
                         float* grad_relation_chunk, kge_stream_t stream);
+
+/* pRotatE only: gradient of the trainable scalar `modulus` (mkb/models/protate.py:72,91;
+ * score = gamma - modulus * sum_d |sin(phase_d)|), which autograd produces at
+ * mkb/compose/pipeline.py:236 next to the table gradients:
+ *   grad_modulus[0] += scale * sum_k grad_scores[k] * (scores[k] - gamma) / modulus
+ * over n scores saved from the forward.  stats != NULL: scale = (grad_loss ? *grad_loss : 1) /
+ * (2 * stats[2]) and grad_scores are K2's coef_pos / coef_neg; stats == NULL: scale = 1 and grad_scores
+ * are plain upstream gradients (K1's backward).  One CTA, fixed order. */
+int kge_modulus_grad(const float* scores, const float* grad_scores, int64_t n, const float* stats,
+                     const float* grad_loss, float gamma, const float* modulus, float* grad_modulus,
+                     kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K7  row-sharded entity table: K2 / K3 with every entity row resolved through a table of shard base

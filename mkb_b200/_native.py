@@ -15,7 +15,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KGE_B200_LIB") or os.path.join(_HERE, "lib", "libkge_b200.so")
 
-MODEL_IDS = {"TransE": 0, "DistMult": 1, "ComplEx": 2, "RotatE": 3}
+MODEL_IDS = {"TransE": 0, "DistMult": 1, "ComplEx": 2, "RotatE": 3, "pRotatE": 4}
+ABI_VERSION = 2
 TAIL_BATCH, HEAD_BATCH = 0, 1
 
 
@@ -29,6 +30,7 @@ class KgeTables(C.Structure):
         ("model", C.c_int32),
         ("gamma", C.c_float),
         ("embedding_range", C.c_float),
+        ("modulus", C.c_void_p),  # pRotatE: device scalar; NULL otherwise
     ]
 
 
@@ -65,6 +67,7 @@ PROTOTYPES = {
     "kge_loss_workspace_bytes": (C.c_size_t, [_I64]),
     "kge_adv_loss_fwd": (C.c_int, [_P, _P, _P, _I64, _I64, C.c_float, _P, _P, _P]),
     "kge_adv_loss_bwd": (C.c_int, [_P, _P, _P, _I64, _I64, C.c_float, _P, _P, _P, _P, _P]),
+    "kge_modulus_grad": (C.c_int, [_P, _P, _I64, _P, _P, C.c_float, _P, _P, _P]),
     "kge_kl_div_fwd": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _P]),
     "kge_kl_div_bwd": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _P, _P]),
     "kge_topk_rows": (C.c_int, [_P, _I64, _I64, _I64, C.c_int32, _P, _P, _P]),
@@ -125,7 +128,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)  # AttributeError here = header and library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.kge_abi_version() != 1:
+        if lib.kge_abi_version() != ABI_VERSION:
             raise KgeError("libkge_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -133,7 +133,7 @@ class Pipeline:
                 if fuse:
                     error = ops.fused_adversarial_step(
                         model.spec, model.entity_embedding, model.relation_embedding, sample, negative_sample,
-                        weight, mode, loss.alpha)
+                        weight, mode, loss.alpha, modulus=model.kernel_modulus)
                 else:
                     score = model(sample)
                     negative_score = model(sample=sample, negative_sample=negative_sample, mode=mode)

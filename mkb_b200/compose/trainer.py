@@ -131,6 +131,15 @@ class DeviceTrainer:
         self.mode = mode
         self.packed_records = bool(packed_records) and mode == "colpar"
         self.ent, self.rel = model.entity_embedding.data, model.relation_embedding.data
+        # pRotatE: the trainable scalar modulus joins the step (single-GPU flow only)
+        self.modulus = model.kernel_modulus.data if getattr(model, "kernel_modulus", None) is not None else None
+        if self.modulus is not None:
+            if mode != "single":
+                raise NotImplementedError("pRotatE runs on the single-GPU DeviceTrainer flow only")
+            self.pos_score = torch.empty((max_batch, 1), **f32)
+            self.neg_score = torch.empty((max_batch, K), **f32)
+            self.g_mod = torch.zeros_like(self.modulus)
+            self.m_mod, self.v_mod = torch.zeros_like(self.modulus), torch.zeros_like(self.modulus)
 
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.stats = torch.zeros(4, **f32)
@@ -334,8 +343,11 @@ class DeviceTrainer:
         if h:
             h[0].record()
         packed = self.packed_records
+        mod = self.modulus
         ops.fused_forward_raw(self.spec, self.ent, self.rel, sample, neg, weight, mode, self.alpha, coef_pos,
-                              coef_neg, self._stats_local if packed else self.stats, self.ws)
+                              coef_neg, self._stats_local if packed else self.stats, self.ws,
+                              self.pos_score[:B] if mod is not None else None,
+                              self.neg_score[:B] if mod is not None else None, modulus=mod)
         if h:
             h[1].record()
         self.t += 1
@@ -347,9 +359,13 @@ class DeviceTrainer:
         if h:
             h[2].record()
         ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
-                               self.g_ent, self.g_rel)
+                               self.g_ent, self.g_rel, modulus=mod)
         if h:
             h[3].record()
+        if mod is not None:
+            ops._modulus_grad(self.spec, self.pos_score[:B], coef_pos, mod, self.g_mod, self.stats)
+            ops._modulus_grad(self.spec, self.neg_score[:B], coef_neg, mod, self.g_mod, self.stats)
+            ops.adam_step(mod, self.g_mod, self.m_mod, self.v_mod, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
         if self.distributed:
             parallel.allreduce_gradients(self._gflat, self.group)
         ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)

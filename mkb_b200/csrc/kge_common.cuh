@@ -26,10 +26,11 @@ struct Traits {
   static constexpr int NC = (M == KGE_COMPLEX || M == KGE_ROTATE) ? 2 : 1;
   static constexpr int RC = (M == KGE_COMPLEX) ? 2 : 1;
   static constexpr bool kDistance = (M == KGE_TRANSE || M == KGE_ROTATE);  // score = gamma - acc
+  static constexpr bool kPhase = (M == KGE_PROTATE);  // score = gamma - modulus * acc, rows are phases * pd
 };
 
 __host__ __device__ inline int entity_comps(int model) {
-  return (model == KGE_COMPLEX || model == KGE_ROTATE) ? 2 : 1;
+  return (model == KGE_COMPLEX || model == KGE_ROTATE) ? 2 : 1;  // pRotatE rows are plain D-vectors
 }
 __host__ __device__ inline int relation_comps(int model) { return model == KGE_COMPLEX ? 2 : 1; }
 
@@ -190,16 +191,27 @@ __device__ __forceinline__ void rel_effective(float r_in0, float r_in1, float ph
     // phase = relation / (embedding_range / pi)   (rotate.py:79-81)
     const float phase = __fdiv_rn(r_in0, phase_div);
     sincosf(phase, &r1, &r0);
+  } else if constexpr (M == KGE_PROTATE) {
+    r0 = __fdiv_rn(r_in0, phase_div);  // phase_relation   (protate.py:80)
+    r1 = 0.f;
   } else {
     r0 = r_in0;
     r1 = r_in1;
   }
 }
 
+// pRotatE (protate.py:79-91): every row is turned into a phase x / phase_div first;
+//   tail: (ph_h + ph_r) - ph_t'          head: ph_h' + (ph_r - ph_t) = -((ph_t - ph_r) - ph_h')
+// so with q = ph_a + ph_r (tail) or ph_a - ph_r (head) the element is |sin(q - ph_e)| in both modes
+// (negation is exact and sin is odd).  `pd` (the phase divisor) is only read by that model.
 template <int M, bool HEAD>
 __device__ __forceinline__ void make_query(float a0, float a1, float r0, float r1, float& q0,
-                                           float& q1) {
-  if constexpr (M == KGE_TRANSE) {
+                                           float& q1, float pd = 1.f) {
+  if constexpr (M == KGE_PROTATE) {
+    const float pa = __fdiv_rn(a0, pd);
+    q0 = HEAD ? __fsub_rn(pa, r0) : __fadd_rn(pa, r0);
+    q1 = 0.f;
+  } else if constexpr (M == KGE_TRANSE) {
     // tail: (h + r) - t'   head: h' + (r - t) = h' - (t - r)      (transe.py:70-73)
     q0 = HEAD ? __fsub_rn(a0, r0) : __fadd_rn(a0, r0);
     q1 = 0.f;
@@ -219,8 +231,10 @@ __device__ __forceinline__ void make_query(float a0, float a1, float r0, float r
 
 // One element's contribution to the reduction over the hidden dim.
 template <int M>
-__device__ __forceinline__ float cand_term(float q0, float q1, float e0, float e1) {
-  if constexpr (M == KGE_TRANSE) {
+__device__ __forceinline__ float cand_term(float q0, float q1, float e0, float e1, float pd = 1.f) {
+  if constexpr (M == KGE_PROTATE) {
+    return fabsf(sinf(__fsub_rn(q0, __fdiv_rn(e0, pd))));
+  } else if constexpr (M == KGE_TRANSE) {
     return fabsf(e0 - q0);
   } else if constexpr (M == KGE_DISTMULT) {
     return q0 * e0;
@@ -233,16 +247,25 @@ __device__ __forceinline__ float cand_term(float q0, float q1, float e0, float e
 }
 
 template <int M>
-__device__ __forceinline__ float finish_score(float acc, float gamma) {
+__device__ __forceinline__ float finish_score(float acc, float gamma, float modulus = 1.f) {
+  if constexpr (Traits<M>::kPhase) return __fsub_rn(gamma, __fmul_rn(acc, modulus));  // protate.py:91
   return Traits<M>::kDistance ? gamma - acc : acc;
 }
 
 // Backward of one element given c = dL/dscore: ge = c * ds/de (goes to the candidate's row),
-// dq += c * ds/dq.
+// dq += c * ds/dq.  pRotatE: the caller passes c already multiplied by the modulus.
 template <int M>
 __device__ __forceinline__ void cand_bwd(float q0, float q1, float e0, float e1, float c, float& ge0,
-                                         float& ge1, float& dq0, float& dq1) {
-  if constexpr (M == KGE_TRANSE) {
+                                         float& ge1, float& dq0, float& dq1, float pd = 1.f) {
+  if constexpr (M == KGE_PROTATE) {
+    // s = gamma - m |sin x|, x = q - e / pd:  ds/dx = -m sign(sin x) cos x
+    float sn, cs;
+    sincosf(__fsub_rn(q0, __fdiv_rn(e0, pd)), &sn, &cs);
+    const float g = (sn > 0.f) ? c * cs : ((sn < 0.f) ? -c * cs : 0.f);
+    ge0 = __fdiv_rn(g, pd);  // dx/de = -1/pd
+    ge1 = 0.f;
+    dq0 -= g;
+  } else if constexpr (M == KGE_TRANSE) {
     const float x = e0 - q0;
     const float sg = (x > 0.f) ? c : ((x < 0.f) ? -c : 0.f);  // c * sign(x), sign(0) = 0
     ge0 = -sg;  // s = gamma - |e - q|
@@ -271,8 +294,13 @@ __device__ __forceinline__ void cand_bwd(float q0, float q1, float e0, float e1,
 // Chain dq through q = make_query(a, r): da (fixed entity row), dr (effective relation pair).
 template <int M, bool HEAD>
 __device__ __forceinline__ void query_bwd(float dq0, float dq1, float a0, float a1, float r0, float r1,
-                                          float& da0, float& da1, float& dr0, float& dr1) {
-  if constexpr (M == KGE_TRANSE) {
+                                          float& da0, float& da1, float& dr0, float& dr1, float pd = 1.f) {
+  if constexpr (M == KGE_PROTATE) {  // q = a / pd +- ph_r
+    da0 = __fdiv_rn(dq0, pd);
+    da1 = 0.f;
+    dr0 = HEAD ? -dq0 : dq0;
+    dr1 = 0.f;
+  } else if constexpr (M == KGE_TRANSE) {
     da0 = dq0;
     da1 = 0.f;
     dr0 = HEAD ? -dq0 : dq0;
@@ -304,6 +332,9 @@ __device__ __forceinline__ void rel_bwd(float dr0, float dr1, float r0, float r1
   if constexpr (M == KGE_ROTATE) {
     // (r0, r1) = (cos θ, sin θ): dθ = -sin θ * dcos + cos θ * dsin ; θ = r / phase_div
     g0 = __fdiv_rn(fmaf(r0, dr1, -r1 * dr0), phase_div);
+    g1 = 0.f;
+  } else if constexpr (M == KGE_PROTATE) {
+    g0 = __fdiv_rn(dr0, phase_div);  // ph_r = r / pd
     g1 = 0.f;
   } else {
     g0 = dr0;

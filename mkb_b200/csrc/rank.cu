@@ -24,8 +24,10 @@ constexpr int kTQ = 64, kTE = 64, kDK = 32, kPad = 68;  // tile sizes; padded ro
 
 // acc <- acc (+) term, one fixed instruction sequence shared by every caller
 template <int M>
-__device__ __forceinline__ float cand_acc(float acc, float q0, float q1, float e0, float e1) {
-  if constexpr (M == KGE_TRANSE) {
+__device__ __forceinline__ float cand_acc(float acc, float q0, float q1, float e0, float e1, float pd) {
+  if constexpr (M == KGE_PROTATE) {
+    return __fadd_rn(acc, fabsf(sinf(__fsub_rn(q0, __fdiv_rn(e0, pd)))));
+  } else if constexpr (M == KGE_TRANSE) {
     return __fadd_rn(acc, fabsf(__fsub_rn(e0, q0)));
   } else if constexpr (M == KGE_DISTMULT) {
     return __fmaf_rn(q0, e0, acc);
@@ -52,7 +54,14 @@ struct RankParams {
   int Q, D;
   int ent_stride, rel_stride;
   float gamma, phase_div;
+  const float* modulus;  // pRotatE: device scalar (else null)
 };
+
+template <int M>
+__device__ __forceinline__ float rk_modulus(const RankParams& p) {
+  if constexpr (Traits<M>::kPhase) return __ldg(p.modulus);
+  else return 1.f;
+}
 
 __device__ __forceinline__ int64_t rk_find_key(const int64_t* __restrict__ keys, int64_t n, int64_t key) {
   int64_t lo = 0, hi = n;
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
     const float a0 = fixed[d], a1 = T::NC == 2 ? fixed[p.D + d] : 0.f;
     float r0, r1, q0, q1;
     rel_effective<M>(relrow[d], T::RC == 2 ? relrow[p.D + d] : 0.f, p.phase_div, r0, r1);
-    make_query<M, HEAD>(a0, a1, r0, r1, q0, q1);
+    make_query<M, HEAD>(a0, a1, r0, r1, q0, q1, p.phase_div);
     q[d] = q0;
     if constexpr (T::NC == 2) q[p.D + d] = q1;
   }
@@ -96,8 +105,8 @@ __global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
     const float* e = p.ent + (HEAD ? h : t) * (int64_t)p.ent_stride;
     float acc = 0.f;
     for (int d = 0; d < p.D; ++d)
-      acc = cand_acc<M>(acc, q[d], T::NC == 2 ? q[p.D + d] : 0.f, e[d], T::NC == 2 ? e[p.D + d] : 0.f);
-    p.pos_score[qi] = finish_score<M>(acc, p.gamma);
+      acc = cand_acc<M>(acc, q[d], T::NC == 2 ? q[p.D + d] : 0.f, e[d], T::NC == 2 ? e[p.D + d] : 0.f, p.phase_div);
+    p.pos_score[qi] = finish_score<M>(acc, p.gamma, rk_modulus<M>(p));
     p.ranks[qi] = 1ull;
     int64_t lo = 0, hi = 0;
     if (p.has_filter) {
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = cand_acc<M>(acc[a][b], q0[a], q1[a], e0[b], e1[b]);
+        for (int b = 0; b < 4; ++b) acc[a][b] = cand_acc<M>(acc[a][b], q0[a], q1[a], e0[b], e1[b], p.phase_div);
     }
   }
 
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
       for (int b = 0; b < 4; ++b) {
         const int64_t e = e_base + tx * 4 + b;
         if (e < p.N) {
-          const float s = finish_score<M>(acc[a][b], p.gamma);
+          const float s = finish_score<M>(acc[a][b], p.gamma, rk_modulus<M>(p));
           const bool beats = (s > sp) || (s == sp && e < pos);
           bool filtered = false;
           if ((beats || p.scores_out) && e != pos && hi > lo)
@@ -212,7 +221,8 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
                             const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out,
                             void* workspace, kge_stream_t stream) {
   if (!t || !t->entity || !t->relation || !queries || !ranks || !workspace) return KGE_E_NULL;
-  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (t->model < KGE_TRANSE || t->model > KGE_PROTATE) return KGE_E_MODEL;
+  if (t->model == KGE_PROTATE && !t->modulus) return KGE_E_NULL;
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   if (Q < 0 || Q > INT32_MAX / kTQ || t->hidden_dim <= 0 || t->n_entity <= 0) return KGE_E_SIZE;
   if (Q == 0) return KGE_OK;
@@ -229,6 +239,7 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
   p.rel_stride = t->hidden_dim * relation_comps(t->model);
   p.gamma = t->gamma;
   p.phase_div = host_phase_div(t->embedding_range);
+  p.modulus = t->modulus;
   char* ws = reinterpret_cast<char*>(workspace);
   p.seg = reinterpret_cast<int64_t*>(ws);
   ws += (size_t)Q * 2 * sizeof(int64_t);
@@ -258,6 +269,7 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
     KGE_CASE(KGE_DISTMULT)
     KGE_CASE(KGE_COMPLEX)
     KGE_CASE(KGE_ROTATE)
+    KGE_CASE(KGE_PROTATE)
   }
 #undef KGE_CASE
   KGE_LAUNCH_CHECK();

@@ -50,6 +50,7 @@ struct FwdParams {
   int ent_stride, rel_stride;
   int k_per_cta;
   float gamma, phase_div, alpha;
+  const float* modulus;  // pRotatE: device scalar (else null)
   // K7 (row-sharded entity table): base pointer of every shard (local HBM or an NVLink peer mapping).
   // Appended last so the unsharded kernels read their parameters at unchanged offsets.
   const float* shard[KGE_MAX_SHARDS];
@@ -64,6 +65,13 @@ __device__ __forceinline__ const float* ent_row(const P& p, int64_t sid) {
   } else {
     return p.ent + sid * (int64_t)p.ent_stride;
   }
+}
+
+// pRotatE's trainable modulus (1 for every other model: folded away at compile time)
+template <int M, typename P>
+__device__ __forceinline__ float load_modulus(const P& p) {
+  if constexpr (Traits<M>::kPhase) return __ldg(p.modulus);
+  else return 1.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -93,12 +101,12 @@ __global__ void __launch_bounds__(kThreads) score_pos_kernel(FwdParams p) {
     for (int v = 0; v < VEC; ++v) {
       float r0, r1, q0, q1;
       rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0, r1);
-      make_query<M, false>(h0[v], h1[v], r0, r1, q0, q1);
-      acc += cand_term<M>(q0, q1, t0[v], t1[v]);
+      make_query<M, false>(h0[v], h1[v], r0, r1, q0, q1, p.phase_div);
+      acc += cand_term<M>(q0, q1, t0[v], t1[v], p.phase_div);
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) p.pos_score[i] = finish_score<M>(acc, p.gamma);
+  if (lane == 0) p.pos_score[i] = finish_score<M>(acc, p.gamma, load_modulus<M>(p));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) score_pos_kernel(FwdParams p) {
 // ------------------------------------------------------------------------------------------------
 template <int M, int VEC, int R, int U>
 __device__ __forceinline__ void rows_reduce(const float* const (&row)[R], const float* __restrict__ q, int D,
-                                            int Dp, int lane, float (&out)[R]) {
+                                            int Dp, int lane, float (&out)[R], float pd) {
   using T = Traits<M>;
   float acc[R];
 #pragma unroll
@@ -138,7 +146,7 @@ __device__ __forceinline__ void rows_reduce(const float* const (&row)[R], const 
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
-            acc[r] += cand_term<M>(q0[v], q1[v], e0[r][u][v], T::NC == 2 ? e1[r][u][v] : 0.f);
+            acc[r] += cand_term<M>(q0[v], q1[v], e0[r][u][v], T::NC == 2 ? e1[r][u][v] : 0.f, pd);
       }
     }
   }
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0[v], r1[v]);
-      make_query<M, HEAD>(a0[v], a1[v], r0[v], r1[v], q0[v], q1[v]);
+      make_query<M, HEAD>(a0[v], a1[v], r0[v], r1[v], q0[v], q1[v], p.phase_div);
     }
     st_shared<VEC>(q + d, q0);
     if constexpr (T::NC == 2) st_shared<VEC>(q + p.Dp + d, q1);
@@ -195,18 +203,18 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           float qp0, qp1;
-          make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1);
-          pacc += cand_term<M>(qp0, qp1, t0[v], t1[v]);
+          make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1, p.phase_div);
+          pacc += cand_term<M>(qp0, qp1, t0[v], t1[v], p.phase_div);
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) pacc += cand_term<M>(q0[v], q1[v], t0[v], t1[v]);
+        for (int v = 0; v < VEC; ++v) pacc += cand_term<M>(q0[v], q1[v], t0[v], t1[v], p.phase_div);
       }
     }
   }
   float pos = 0.f;
   if (want_pos) {  // uniform across the CTA
-    pos = finish_score<M>(block_sum(pacc, red), p.gamma);
+    pos = finish_score<M>(block_sum(pacc, red), p.gamma, load_modulus<M>(p));
     if (tid == 0 && p.pos_score) p.pos_score[i] = pos;
   }
   __syncthreads();
@@ -228,13 +236,13 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
         rows[r] = ent_row<SHARD>(p, id);
       }
       float acc[R];
-      rows_reduce<M, VEC, R, U>(rows, q, p.D, p.Dp, lane, acc);
+      rows_reduce<M, VEC, R, U>(rows, q, p.D, p.Dp, lane, acc, p.phase_div);
       if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (m + r < cnt) {
             const int j = jb + (m + r) * kWarps;
-            const float s = finish_score<M>(acc[r], p.gamma);
+            const float s = finish_score<M>(acc[r], p.gamma, load_modulus<M>(p));
             if (p.neg_score) p.neg_score[i * (int64_t)p.K + j] = s;
             if constexpr (FUSED) sc[j] = s;
           }
@@ -287,6 +295,7 @@ struct BwdParams {
   int rec_B, n_rec;
   long long rec_stride;
   float phase_div;
+  const float* modulus;  // pRotatE: device scalar (else null)
   // K7 (row-sharded entity table): table shards to read, gradient shards to add into (appended last)
   const float* shard[KGE_MAX_SHARDS];
   float* gshard[KGE_MAX_SHARDS];
@@ -347,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       wsum += __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.stats) + (size_t)r * p.rec_stride) + 2);
     scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * wsum);
   }
+  scale *= load_modulus<M>(p);  // pRotatE: the element derivatives below are those of sum |sin|
   const bool do_pos = (p.gpos != nullptr) && blockIdx.y == 0;
   const float cpos =
       do_pos ? scale * __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.gpos) + roff) + i) : 0.f;
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       for (int v = 0; v < VEC; ++v) {
         float r0, r1;
         rel_effective<M>(rr0[v], rr1[v], p.phase_div, r0, r1);
-        make_query<M, HEAD>(a0[v], a1[v], r0, r1, q0[v], q1[v]);
+        make_query<M, HEAD>(a0[v], a1[v], r0, r1, q0[v], q1[v], p.phase_div);
       }
     }
     // ---- candidates: group g takes every G-th row of the tile
@@ -405,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
 #pragma unroll
               for (int v = 0; v < VEC; ++v)
                 cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
-                            dq0[v], dq1[v]);
+                            dq0[v], dq1[v], p.phase_div);
               red_row<VEC, SHARD>(p, grow + d, g0);
               if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
             }
@@ -464,25 +474,25 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             float qp0, qp1;
-            make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1);
-            cand_bwd<M>(qp0, qp1, t0[v], t1[v], cpos, gt0[v], gt1[v], dqp0[v], dqp1[v]);
+            make_query<M, false>(h0[v], h1[v], r0[v], r1[v], qp0, qp1, p.phase_div);
+            cand_bwd<M>(qp0, qp1, t0[v], t1[v], cpos, gt0[v], gt1[v], dqp0[v], dqp1[v], p.phase_div);
           }
         } else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
-            cand_bwd<M>(q0[v], q1[v], t0[v], t1[v], cpos, gt0[v], gt1[v], dq0[v], dq1[v]);
+            cand_bwd<M>(q0[v], q1[v], t0[v], t1[v], cpos, gt0[v], gt1[v], dq0[v], dq1[v], p.phase_div);
         }
       }
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         float da0, da1, dr0, dr1;
-        query_bwd<M, HEAD>(dq0[v], dq1[v], a0[v], a1[v], r0[v], r1[v], da0, da1, dr0, dr1);
+        query_bwd<M, HEAD>(dq0[v], dq1[v], a0[v], a1[v], r0[v], r1[v], da0, da1, dr0, dr1, p.phase_div);
         if constexpr (HEAD) {
           gt0[v] += da0;
           gt1[v] += da1;
           if (do_pos) {
             float dh0, dh1, dpr0, dpr1;
-            query_bwd<M, false>(dqp0[v], dqp1[v], h0[v], h1[v], r0[v], r1[v], dh0, dh1, dpr0, dpr1);
+            query_bwd<M, false>(dqp0[v], dqp1[v], h0[v], h1[v], r0[v], r1[v], dh0, dh1, dpr0, dpr1, p.phase_div);
             gh0[v] = dh0;
             gh1[v] = dh1;
             dr0 += dpr0;
@@ -516,7 +526,8 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
 // ------------------------------------------------------------------------------------------------
 static int validate_tables(const kge_tables_t* t) {
   if (!t || !t->entity || !t->relation) return KGE_E_NULL;
-  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (t->model < KGE_TRANSE || t->model > KGE_PROTATE) return KGE_E_MODEL;
+  if (t->model == KGE_PROTATE && !t->modulus) return KGE_E_NULL;
   if (t->hidden_dim <= 0 || t->n_entity <= 0 || t->n_relation <= 0) return KGE_E_SIZE;
   if ((reinterpret_cast<uintptr_t>(t->entity) | reinterpret_cast<uintptr_t>(t->relation)) & 3u)
     return KGE_E_ALIGN;
@@ -570,6 +581,7 @@ static int dispatch_neg(int model, int mode, bool vec, const FwdParams& p, dim3 
     KGE_CASE(KGE_DISTMULT)
     KGE_CASE(KGE_COMPLEX)
     KGE_CASE(KGE_ROTATE)
+    KGE_CASE(KGE_PROTATE)
   }
 #undef KGE_CASE
   return KGE_E_MODEL;
@@ -588,6 +600,7 @@ static int dispatch_neg_sharded(int model, int mode, const FwdParams& p, dim3 gr
     KGE_CASE(KGE_DISTMULT)
     KGE_CASE(KGE_COMPLEX)
     KGE_CASE(KGE_ROTATE)
+    KGE_CASE(KGE_PROTATE)
   }
 #undef KGE_CASE
   return KGE_E_MODEL;
@@ -596,7 +609,8 @@ static int dispatch_neg_sharded(int model, int mode, const FwdParams& p, dim3 gr
 // Argument checks shared by the sharded entry points; fills the kernel-side pointer tables.
 static int validate_sharded(const kge_tables_t* t, const kge_shards_t* sh, bool need_grad) {
   if (!t || !t->relation || !sh) return KGE_E_NULL;
-  if (t->model < KGE_TRANSE || t->model > KGE_ROTATE) return KGE_E_MODEL;
+  if (t->model < KGE_TRANSE || t->model > KGE_PROTATE) return KGE_E_MODEL;
+  if (t->model == KGE_PROTATE && !t->modulus) return KGE_E_NULL;
   if (t->hidden_dim <= 0 || t->n_entity <= 0 || t->n_relation <= 0 || t->n_entity > INT32_MAX) return KGE_E_SIZE;
   if (sh->n_shards < 1 || sh->n_shards > KGE_MAX_SHARDS) return KGE_E_SIZE;
   if (t->hidden_dim % 4 != 0) return KGE_E_UNSUPPORTED;
@@ -621,6 +635,7 @@ static void fill_fwd(FwdParams& p, const kge_tables_t* t, const kge_shards_t* sh
   p.rel_stride = t->hidden_dim * relation_comps(t->model);
   p.gamma = t->gamma;
   p.phase_div = host_phase_div(t->embedding_range);
+  p.modulus = t->modulus;
 }
 
 template <int M, bool HEAD, int VEC, bool SHARD = false>
@@ -680,6 +695,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.g_ent_stride = p.D * entity_comps(t->model);
   p.g_rel_stride = p.D * relation_comps(t->model);
   p.phase_div = host_phase_div(t->embedding_range);
+  p.modulus = t->modulus;
   const bool vec = sh ? aligned16(grad_rel)  // validate_sharded checked the rest
                       : can_vectorize(t, grad_ent, grad_rel) && (p.col0 % 4 == 0) && (p.D % 4 == 0);
   if (sh && !vec) return KGE_E_ALIGN;
@@ -717,6 +733,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
       KGE_CASE(KGE_DISTMULT)
       KGE_CASE(KGE_COMPLEX)
       KGE_CASE(KGE_ROTATE)
+      KGE_CASE(KGE_PROTATE)
     }
 #undef KGE_CASE
     return KGE_E_MODEL;
@@ -731,6 +748,7 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
     KGE_CASE(KGE_DISTMULT)
     KGE_CASE(KGE_COMPLEX)
     KGE_CASE(KGE_ROTATE)
+    KGE_CASE(KGE_PROTATE)
   }
 #undef KGE_CASE
   return KGE_E_MODEL;
@@ -768,6 +786,7 @@ extern "C" int kge_score_fwd(const kge_tables_t* t, int mode, const int64_t* sam
       KGE_CASE(KGE_DISTMULT)
       KGE_CASE(KGE_COMPLEX)
       KGE_CASE(KGE_ROTATE)
+      KGE_CASE(KGE_PROTATE)
     }
 #undef KGE_CASE
     KGE_LAUNCH_CHECK();
@@ -894,6 +913,7 @@ extern "C" int kge_score_fwd_sharded(const kge_tables_t* t, const kge_shards_t* 
       case KGE_DISTMULT: score_pos_kernel<KGE_DISTMULT, 4, true><<<grid, kThreads, 0, st>>>(p); break;
       case KGE_COMPLEX: score_pos_kernel<KGE_COMPLEX, 4, true><<<grid, kThreads, 0, st>>>(p); break;
       case KGE_ROTATE: score_pos_kernel<KGE_ROTATE, 4, true><<<grid, kThreads, 0, st>>>(p); break;
+      case KGE_PROTATE: score_pos_kernel<KGE_PROTATE, 4, true><<<grid, kThreads, 0, st>>>(p); break;
     }
     KGE_LAUNCH_CHECK();
     return KGE_OK;
@@ -952,4 +972,39 @@ extern "C" int kge_fused_bwd_sharded(const kge_tables_t* t, const kge_shards_t* 
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, nullptr, grad_relation,
                  (cudaStream_t)stream, 0, 0, 1, 0, sh);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pRotatE's trainable modulus (mkb/models/protate.py:72,91): score = gamma - modulus * A with
+// A = sum_d |sin(phase)|, so dL/dmodulus = sum_k dL/dscore_k * (-A_k) = sum_k g_k (score_k - gamma) / modulus.
+// One CTA, fixed summation order (deterministic); ADDS into grad_modulus[0].
+// ------------------------------------------------------------------------------------------------
+namespace kge {
+__global__ void __launch_bounds__(kThreads) modulus_grad_kernel(const float* __restrict__ scores,
+                                                                const float* __restrict__ grad_scores, int64_t n,
+                                                                const float* __restrict__ stats,
+                                                                const float* __restrict__ grad_loss, float gamma,
+                                                                const float* __restrict__ modulus,
+                                                                float* grad_modulus) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  for (int64_t k = threadIdx.x; k < n; k += kThreads) acc = fmaf(grad_scores[k], scores[k] - gamma, acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float scale = stats ? (grad_loss ? __ldg(grad_loss) : 1.f) / (2.f * __ldg(stats + 2)) : 1.f;
+    grad_modulus[0] += scale * acc / __ldg(modulus);
+  }
+}
+}  // namespace kge
+
+extern "C" int kge_modulus_grad(const float* scores, const float* grad_scores, int64_t n, const float* stats,
+                                const float* grad_loss, float gamma, const float* modulus, float* grad_modulus,
+                                kge_stream_t stream) {
+  if (!scores || !grad_scores || !modulus || !grad_modulus) return KGE_E_NULL;
+  if (n < 0) return KGE_E_SIZE;
+  if (n == 0) return KGE_OK;
+  modulus_grad_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(scores, grad_scores, n, stats, grad_loss, gamma,
+                                                               modulus, grad_modulus);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
 }

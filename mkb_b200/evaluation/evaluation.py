@@ -100,7 +100,8 @@ class Evaluation:
         csr = self._filter("head" if mode == "head-batch" else "tail", dev)
         chunk = max(int(self.batch_size), 1) * 64  # rank tiles are 64 queries; keep launches large
         out = [ops.rank_all(model.spec, model.entity_embedding, model.relation_embedding, queries[lo:lo + chunk],
-                            mode, csr) for lo in range(0, queries.shape[0], chunk)]
+                            mode, csr, modulus=getattr(model, "kernel_modulus", None))
+               for lo in range(0, queries.shape[0], chunk)]
         return torch.cat(out) if out else torch.zeros(0, dtype=torch.int64, device=dev)
 
     @staticmethod

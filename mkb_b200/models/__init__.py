@@ -1,4 +1,4 @@
 from .base import BaseModel
-from .kge import ComplEx, DistMult, RotatE, TransE
+from .kge import ComplEx, DistMult, RotatE, TransE, pRotatE
 
-__all__ = ["BaseModel", "ComplEx", "DistMult", "RotatE", "TransE"]
+__all__ = ["BaseModel", "ComplEx", "DistMult", "RotatE", "TransE", "pRotatE"]

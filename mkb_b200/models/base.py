@@ -103,6 +103,12 @@ class BaseModel(nn.Module):
             self._spec = ops.TableSpec(self.name, self.hidden_dim, self.gamma.item(), self.embedding_range.item())
         return self._spec
 
+    @property
+    def kernel_modulus(self):
+        """The modulus the kernels read: pRotatE's trainable scalar, None for every other model (RotatE
+        carries an unused one, rotate.py:66-67)."""
+        return self.modulus if self.name == "pRotatE" else None
+
     def forward(self, sample, negative_sample=None, mode=None):
         """``model(sample)``, ``model(sample, negative_sample, mode)``, ``model(sample[n,b,3])``
         (mkb/models/base.py:153-207 + transe.py:65-76 / distmult.py:63-75 / complex.py:65-85 /
@@ -110,5 +116,6 @@ class BaseModel(nn.Module):
         flat, shape = self.format_sample(sample, negative_sample)
         if sample.dim() == 3:
             negative_sample, mode = None, None
-        out = ops.score(self.spec, self.entity_embedding, self.relation_embedding, flat, negative_sample, mode)
+        out = ops.score(self.spec, self.entity_embedding, self.relation_embedding, flat, negative_sample, mode,
+                        self.kernel_modulus)
         return out.view(shape)

@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from .base import BaseModel
 
-__all__ = ["TransE", "DistMult", "ComplEx", "RotatE"]
+__all__ = ["TransE", "DistMult", "ComplEx", "RotatE", "pRotatE"]
 
 
 class TransE(BaseModel):
@@ -30,6 +30,17 @@ class RotatE(BaseModel):
     (rotate.py:66-67): trainable, never used, its grad stays None."""
 
     _entity_mult = 2
+
+    def __init__(self, hidden_dim, entities, relations, gamma):
+        super().__init__(hidden_dim=hidden_dim, entities=entities, relations=relations, gamma=gamma)
+        self.pi = pi
+        self.modulus = nn.Parameter(torch.Tensor([[0.5 * self.embedding_range.item()]]))
+
+
+class pRotatE(BaseModel):
+    """score = gamma - modulus * sum_d | sin((h + r - t) / (range / pi)) | — RotatE on phases only, with a
+    TRAINABLE scalar ``modulus`` initialised to 0.5 * range (mkb/models/protate.py:60-93).  Runs on the
+    same kernel template as the other models; the modulus is read on the device."""
 
     def __init__(self, hidden_dim, entities, relations, gamma):
         super().__init__(hidden_dim=hidden_dim, entities=entities, relations=relations, gamma=gamma)

@@ -28,7 +28,18 @@ class TableSpec:
         self.gamma = float(gamma)
         self.embedding_range = float(embedding_range)
 
-    def struct(self, ent, rel):
+    def _modulus_ptr(self, modulus):
+        """pRotatE reads its trainable modulus on the device (kge_tables_t.modulus)."""
+        if self.model_name != "pRotatE":
+            return None
+        if modulus is None:
+            raise ValueError("pRotatE needs its modulus tensor")
+        N.require_cuda(modulus)
+        if modulus.dtype != torch.float32 or modulus.numel() != 1:
+            raise TypeError("modulus must be a float32 tensor with one element")
+        return modulus.data_ptr()
+
+    def struct(self, ent, rel, modulus=None):
         nc = 2 if self.model_name in ("ComplEx", "RotatE") else 1
         rc = 2 if self.model_name == "ComplEx" else 1
         if ent.shape[1] != nc * self.hidden_dim or rel.shape[1] != rc * self.hidden_dim:
@@ -36,16 +47,16 @@ class TableSpec:
                 f"{self.model_name}: table shapes {tuple(ent.shape)}/{tuple(rel.shape)} do not match "
                 f"hidden_dim={self.hidden_dim}")
         return N.KgeTables(ent.data_ptr(), rel.data_ptr(), ent.shape[0], rel.shape[0], self.hidden_dim,
-                           self.model_id, self.gamma, self.embedding_range)
+                           self.model_id, self.gamma, self.embedding_range, self._modulus_ptr(modulus))
 
-    def struct_sharded(self, n_entity, rel):
+    def struct_sharded(self, n_entity, rel, modulus=None):
         """Tables struct of a row-sharded model: no local entity table, the GLOBAL entity count."""
         rc = 2 if self.model_name == "ComplEx" else 1
         if rel.shape[1] != rc * self.hidden_dim:
             raise ValueError(f"{self.model_name}: relation table {tuple(rel.shape)} does not match "
                              f"hidden_dim={self.hidden_dim}")
         return N.KgeTables(None, rel.data_ptr(), int(n_entity), rel.shape[0], self.hidden_dim, self.model_id,
-                           self.gamma, self.embedding_range)
+                           self.gamma, self.embedding_range, self._modulus_ptr(modulus))
 
     @property
     def entity_dim(self):
@@ -77,12 +88,21 @@ def _prep_ids(t, device):
 # ---------------------------------------------------------------------------------------------
 # K1 score (+ autograd)
 # ---------------------------------------------------------------------------------------------
-def _score_fwd(spec, ent, rel, sample, neg, mode):
+def _modulus_grad(spec, scores, grad_scores, modulus, out, stats=None, grad_loss=None):
+    """out[0] += d/dmodulus of sum(grad_scores * scores) (pRotatE; kge_modulus_grad)."""
+    lib = N.load()
+    N.check(lib.kge_modulus_grad(N.ptr(scores), N.ptr(grad_scores), scores.numel(), N.ptr(stats), N.ptr(grad_loss),
+                                 spec.gamma, N.ptr(modulus), N.ptr(out), N.stream_ptr(scores.device)),
+            "kge_modulus_grad")
+    N.count_launch()
+
+
+def _score_fwd(spec, ent, rel, sample, neg, mode, modulus=None):
     lib = N.load()
     B = sample.shape[0]
     K = 1 if neg is None else neg.shape[1]
     out = torch.empty((B, K), dtype=torch.float32, device=ent.device)
-    tb = spec.struct(ent, rel)
+    tb = spec.struct(ent, rel, modulus)
     N.check(lib.kge_score_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg),
                               0 if neg is None else K, N.ptr(out), N.stream_ptr(ent.device)),
             "kge_score_fwd")
@@ -92,34 +112,41 @@ def _score_fwd(spec, ent, rel, sample, neg, mode):
 
 class _ScoreFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ent, rel, sample, neg, mode, spec):
+    def forward(ctx, ent, rel, sample, neg, mode, spec, modulus):
         ent_c, rel_c = _prep_tables(ent, rel)
-        ctx.save_for_backward(ent_c, rel_c, sample, neg)
-        ctx.mode, ctx.spec = mode, spec
+        mod_c = modulus.detach() if modulus is not None else None
         with torch.cuda.device(ent.device):
-            return _score_fwd(spec, ent_c, rel_c, sample, neg, mode)
+            out = _score_fwd(spec, ent_c, rel_c, sample, neg, mode, mod_c)
+        # pRotatE keeps its scores: d score / d modulus = (score - gamma) / modulus
+        ctx.save_for_backward(ent_c, rel_c, sample, neg, mod_c, out if mod_c is not None else None)
+        ctx.mode, ctx.spec = mode, spec
+        return out
 
     @staticmethod
     def backward(ctx, grad_scores):
-        ent, rel, sample, neg = ctx.saved_tensors
+        ent, rel, sample, neg, modulus, out = ctx.saved_tensors
         lib = N.load()
         g = grad_scores.contiguous().float()
         # index_select's backward yields dense gradients: same contract here
         g_ent = torch.zeros_like(ent)
         g_rel = torch.zeros_like(rel)
-        tb = ctx.spec.struct(ent, rel)
+        tb = ctx.spec.struct(ent, rel, modulus)
         B = sample.shape[0]
+        g_mod = None
         with torch.cuda.device(ent.device):
             N.check(lib.kge_score_bwd(C.byref(tb), _mode_id(ctx.mode), N.ptr(sample), B, N.ptr(neg),
                                       0 if neg is None else neg.shape[1], N.ptr(g), N.ptr(g_ent),
                                       N.ptr(g_rel), N.stream_ptr(ent.device)), "kge_score_bwd")
+            if modulus is not None and ctx.needs_input_grad[6]:
+                g_mod = torch.zeros_like(modulus)
+                _modulus_grad(ctx.spec, out, g, modulus, g_mod)
         N.count_launch()
-        return g_ent, g_rel, None, None, None, None
+        return g_ent, g_rel, None, None, None, None, g_mod
 
 
-def score(spec, ent, rel, sample, neg=None, mode=None):
+def score(spec, ent, rel, sample, neg=None, mode=None, modulus=None):
     """``model(sample[, negative_sample, mode])`` -> float32 ``[B,1]`` / ``[B,K]``, differentiable
-    w.r.t. both tables (mkb/models/base.py:153-207 + the model's forward)."""
+    w.r.t. both tables — and pRotatE's ``modulus`` — (mkb/models/base.py:153-207 + the model's forward)."""
     N.require_cuda(ent, rel, sample, neg)
     sample = _prep_ids(sample, ent.device)
     neg = _prep_ids(neg, ent.device)
@@ -129,7 +156,9 @@ def score(spec, ent, rel, sample, neg=None, mode=None):
         raise ValueError("sample must be [B,3]")
     if neg is not None and (neg.dim() != 2 or neg.shape[0] != sample.shape[0]):
         raise ValueError("negative_sample must be [B,K]")
-    return _ScoreFn.apply(ent, rel, sample, neg, mode, spec)
+    if spec.model_name != "pRotatE":
+        modulus = None
+    return _ScoreFn.apply(ent, rel, sample, neg, mode, spec, modulus)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -263,17 +292,19 @@ def topk_rows(scores, k, return_values=False):
 # ---------------------------------------------------------------------------------------------
 class _FusedStepFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ent, rel, sample, neg, weight, mode, alpha, spec, want_scores):
+    def forward(ctx, ent, rel, sample, neg, weight, mode, alpha, spec, want_scores, modulus):
         lib = N.load()
         ent_c, rel_c = _prep_tables(ent, rel)
+        mod_c = modulus.detach() if modulus is not None else None
         B, K = neg.shape
         dev = ent.device
         coef_pos = torch.empty(B, dtype=torch.float32, device=dev)
         coef_neg = torch.empty((B, K), dtype=torch.float32, device=dev)
         stats = torch.empty(4, dtype=torch.float32, device=dev)
-        pos_s = torch.empty((B, 1), dtype=torch.float32, device=dev) if want_scores else None
-        neg_s = torch.empty((B, K), dtype=torch.float32, device=dev) if want_scores else None
-        tb = spec.struct(ent_c, rel_c)
+        keep_scores = want_scores or mod_c is not None  # pRotatE's modulus gradient needs them
+        pos_s = torch.empty((B, 1), dtype=torch.float32, device=dev) if keep_scores else None
+        neg_s = torch.empty((B, K), dtype=torch.float32, device=dev) if keep_scores else None
+        tb = spec.struct(ent_c, rel_c, mod_c)
         with torch.cuda.device(dev):
             ws = _loss_workspace(B, dev)
             N.check(lib.kge_fused_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K,
@@ -281,7 +312,8 @@ class _FusedStepFn(torch.autograd.Function):
                                       N.ptr(coef_neg), N.ptr(stats), N.ptr(ws), N.stream_ptr(dev)),
                     "kge_fused_fwd")
         N.count_launch()
-        ctx.save_for_backward(ent_c, rel_c, sample, neg, coef_pos, coef_neg, stats)
+        ctx.save_for_backward(ent_c, rel_c, sample, neg, coef_pos, coef_neg, stats, mod_c,
+                              pos_s if mod_c is not None else None, neg_s if mod_c is not None else None)
         ctx.mode, ctx.spec = mode, spec
         loss = stats[3].clone()
         if want_scores:
@@ -291,23 +323,29 @@ class _FusedStepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss, *_):
-        ent, rel, sample, neg, coef_pos, coef_neg, stats = ctx.saved_tensors
+        ent, rel, sample, neg, coef_pos, coef_neg, stats, modulus, pos_s, neg_s = ctx.saved_tensors
         lib = N.load()
         g_ent = torch.zeros_like(ent)
         g_rel = torch.zeros_like(rel)
         gl = grad_loss.contiguous().float()
-        tb = ctx.spec.struct(ent, rel)
+        tb = ctx.spec.struct(ent, rel, modulus)
         B, K = neg.shape
+        g_mod = None
         with torch.cuda.device(ent.device):
             N.check(lib.kge_fused_bwd(C.byref(tb), _mode_id(ctx.mode), N.ptr(sample), B, N.ptr(neg), K,
                                       N.ptr(coef_pos), N.ptr(coef_neg), N.ptr(stats), N.ptr(gl),
                                       N.ptr(g_ent), N.ptr(g_rel), N.stream_ptr(ent.device)),
                     "kge_fused_bwd")
+            if modulus is not None and ctx.needs_input_grad[9]:
+                g_mod = torch.zeros_like(modulus)
+                _modulus_grad(ctx.spec, pos_s, coef_pos, modulus, g_mod, stats, gl)
+                _modulus_grad(ctx.spec, neg_s, coef_neg, modulus, g_mod, stats, gl)
         N.count_launch()
-        return g_ent, g_rel, None, None, None, None, None, None, None
+        return g_ent, g_rel, None, None, None, None, None, None, None, g_mod
 
 
-def fused_adversarial_step(spec, ent, rel, sample, neg, weight, mode, alpha=0.5, return_scores=False):
+def fused_adversarial_step(spec, ent, rel, sample, neg, weight, mode, alpha=0.5, return_scores=False,
+                           modulus=None):
     """``loss(model(sample), model(sample, neg, mode), weight)`` (mkb/compose/pipeline.py:211-234) as
     ONE forward kernel; ``.backward()`` on the result launches ONE backward kernel."""
     N.require_cuda(ent, rel, sample, neg, weight)
@@ -318,14 +356,16 @@ def fused_adversarial_step(spec, ent, rel, sample, neg, weight, mode, alpha=0.5,
     weight = weight.to(device=ent.device, dtype=torch.float32).contiguous().view(-1)
     if neg.dim() != 2 or neg.shape[0] != sample.shape[0] or weight.shape[0] != sample.shape[0]:
         raise ValueError("shape mismatch between sample, negative_sample and weight")
-    return _FusedStepFn.apply(ent, rel, sample, neg, weight, mode, float(alpha), spec, bool(return_scores))
+    if spec.model_name != "pRotatE":
+        modulus = None
+    return _FusedStepFn.apply(ent, rel, sample, neg, weight, mode, float(alpha), spec, bool(return_scores), modulus)
 
 
 def fused_forward_raw(spec, ent, rel, sample, neg, weight, mode, alpha, coef_pos, coef_neg, stats, ws,
-                      pos_score=None, neg_score=None):
+                      pos_score=None, neg_score=None, modulus=None):
     """Autograd-free K2 launch into caller-owned buffers (the device-resident training loop)."""
     lib = N.load()
-    tb = spec.struct(ent, rel)
+    tb = spec.struct(ent, rel, modulus)
     B, K = neg.shape
     N.check(lib.kge_fused_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K, N.ptr(weight),
                               alpha, N.ptr(pos_score), N.ptr(neg_score), N.ptr(coef_pos), N.ptr(coef_neg),
@@ -334,10 +374,10 @@ def fused_forward_raw(spec, ent, rel, sample, neg, weight, mode, alpha, coef_pos
 
 
 def fused_backward_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, g_ent, g_rel,
-                       grad_loss=None):
+                       grad_loss=None, modulus=None):
     """Autograd-free K3 launch: ADDS into g_ent / g_rel."""
     lib = N.load()
-    tb = spec.struct(ent, rel)
+    tb = spec.struct(ent, rel, modulus)
     B, K = neg.shape
     N.check(lib.kge_fused_bwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K, N.ptr(coef_pos),
                               N.ptr(coef_neg), N.ptr(stats), N.ptr(grad_loss), N.ptr(g_ent), N.ptr(g_rel),
@@ -557,7 +597,7 @@ def filter_pool(csr, sample, mode, size, n_entity, pool, status=None, out=None):
 # ---------------------------------------------------------------------------------------------
 # K5 ranking
 # ---------------------------------------------------------------------------------------------
-def rank_all(spec, ent, rel, queries, mode, csr=None, return_scores=False):
+def rank_all(spec, ent, rel, queries, mode, csr=None, return_scores=False, modulus=None):
     """Filtered rank of the true entity for every query (int64 ``[Q]``)."""
     lib = N.load()
     ent, rel = _prep_tables(ent.detach(), rel.detach())
@@ -566,7 +606,7 @@ def rank_all(spec, ent, rel, queries, mode, csr=None, return_scores=False):
     dev = ent.device
     ranks = torch.empty(Q, dtype=torch.int64, device=dev)
     scores = torch.empty((Q, ent.shape[0]), dtype=torch.float32, device=dev) if return_scores else None
-    tb = spec.struct(ent, rel)
+    tb = spec.struct(ent, rel, modulus.detach() if modulus is not None else None)
     ws = torch.empty(max(lib.kge_rank_workspace_bytes(C.byref(tb), Q), 8), dtype=torch.uint8, device=dev)
     fs = csr.to(dev).struct() if csr is not None else None
     with torch.cuda.device(dev):

@@ -35,19 +35,23 @@ def ok(rc, what=""):
     assert rc == 0, f"{what} returned {rc}: {lib().kge_strerror(rc).decode()}"
 
 
-NC = {"TransE": 1, "DistMult": 1, "ComplEx": 2, "RotatE": 2}
-RC = {"TransE": 1, "DistMult": 1, "ComplEx": 2, "RotatE": 1}
+NC = {"TransE": 1, "DistMult": 1, "ComplEx": 2, "RotatE": 2, "pRotatE": 1}
+RC = {"TransE": 1, "DistMult": 1, "ComplEx": 2, "RotatE": 1, "pRotatE": 1}
 
 
 def mode_id(mode):
     return N.HEAD_BATCH if mode == "head-batch" else N.TAIL_BATCH
 
 
-def tables(model, ent, rel, gamma, n_entity=None):
+def tables(model, ent, rel, gamma, n_entity=None, modulus=None):
     D = rel.shape[1] // RC[model]
     rng = np.float32((np.float32(gamma) + np.float32(2)) / np.float32(D))  # (gamma + 2) / D as the model stores it
-    return N.KgeTables(P(ent), P(rel), ent.shape[0] if n_entity is None else n_entity, rel.shape[0], D,
-                       N.MODEL_IDS[model], float(gamma), float(rng))
+    tb = N.KgeTables(P(ent), P(rel), ent.shape[0] if n_entity is None else n_entity, rel.shape[0], D,
+                     N.MODEL_IDS[model], float(gamma), float(rng), None)
+    if modulus is not None:  # pRotatE: a "device" scalar
+        tb._mod = np.array([modulus], dtype=np.float32)
+        tb.modulus = P(tb._mod)
+    return tb
 
 
 def csr_struct(csr):
@@ -87,30 +91,29 @@ def merge_rows(shards, n):
     return out
 
 
-def score(model, ent, rel, gamma, sample, neg=None, mode=None, shards=None):
+def score(model, ent, rel, gamma, sample, neg=None, mode=None, shards=None, modulus=None):
     l = lib()
     B = sample.shape[0]
     K = 1 if neg is None else neg.shape[1]
     out = np.full((B, K), np.nan, dtype=np.float32)
+    tb = tables(model, ent, rel, gamma, modulus=modulus)
     if shards is None:
-        tb = tables(model, ent, rel, gamma)
         ok(l.kge_score_fwd(C.byref(tb), mode_id(mode), P(sample), B, P(neg), 0 if neg is None else K, P(out), None))
     else:
-        tb = tables(model, ent, rel, gamma)
         tb.entity = None
         ok(l.kge_score_fwd_sharded(C.byref(tb), C.byref(shards), mode_id(mode), P(sample), B, P(neg),
                                    0 if neg is None else K, P(out), None))
     return out
 
 
-def fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, alpha=0.5, shards=None):
+def fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, alpha=0.5, shards=None, modulus=None):
     l = lib()
     B, K = neg.shape
     r = dict(pos=np.full((B, 1), np.nan, np.float32), neg=np.full((B, K), np.nan, np.float32),
              cpos=np.full(B, np.nan, np.float32), cneg=np.full((B, K), np.nan, np.float32),
              stats=np.zeros(4, np.float32))
     ws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, dtype=np.uint8)
-    tb = tables(model, ent, rel, gamma)
+    tb = tables(model, ent, rel, gamma, modulus=modulus)
     if shards is None:
         ok(l.kge_fused_fwd(C.byref(tb), mode_id(mode), P(sample), B, P(neg), K, P(w), alpha, P(r["pos"]),
                            P(r["neg"]), P(r["cpos"]), P(r["cneg"]), P(r["stats"]), P(ws), None), "kge_fused_fwd")
@@ -123,11 +126,22 @@ def fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, alpha=0.5, shards=No
     return r
 
 
-def fused_bwd(model, ent, rel, gamma, sample, neg, mode, f, shards=None, grad_loss=None):
+def modulus_grad(f, gamma, modulus, grad_loss=None):
+    """dL/dmodulus of a fused step from its saved scores and coefficients (two kge_modulus_grad calls)."""
+    l = lib()
+    out = np.zeros(1, np.float32)
+    mod = np.array([modulus], np.float32)
+    gl = None if grad_loss is None else np.array([grad_loss], np.float32)
+    for sc, co in ((f["pos"], f["cpos"]), (f["neg"], f["cneg"])):
+        ok(l.kge_modulus_grad(P(sc), P(co), sc.size, P(f["stats"]), P(gl), float(gamma), P(mod), P(out), None))
+    return float(out[0])
+
+
+def fused_bwd(model, ent, rel, gamma, sample, neg, mode, f, shards=None, grad_loss=None, modulus=None):
     l = lib()
     B, K = neg.shape
     g_rel = np.zeros_like(rel)
-    tb = tables(model, ent, rel, gamma)
+    tb = tables(model, ent, rel, gamma, modulus=modulus)
     gl = None if grad_loss is None else np.array([grad_loss], np.float32)
     if shards is None:
         g_ent = np.zeros_like(ent)

@@ -342,3 +342,70 @@ def test_topk_rows_matches_stable_argsort(cols, k):
         np.testing.assert_array_equal(val[r], x[r, ref])
     assert l.kge_topk_rows(H.P(x), rows, cols, cols + 3, cols + 1, H.P(idx), None, None) == -2
     assert l.kge_topk_rows(H.P(x), rows, 5000, 5000, 1025, H.P(idx), None, None) == -6
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("D,B,K", [(16, 5, 19), (5, 3, 7), (132, 2, 40)])
+def test_protate_fused_step_vs_oracle(mode, D, B, K):
+    """pRotatE through the same kernel template: scores, loss, table gradients, modulus gradient
+    (fused and unfused routes), incl. the row-sharded variants."""
+    l = H.lib()
+    Nn, R, gamma, mod = 60, 4, 9.0, 0.37
+    ent, rel, sample, neg, w = _problem("pRotatE", Nn, R, D, B, K, seed=D + B)
+    ent *= 4.0  # phases well outside (-pi/2, pi/2)
+    loss, pos, ngs, ge, gr, gm = ko.train_step("pRotatE", ent, rel, sample, neg, mode, w, gamma=gamma, modulus=mod)
+    f = H.fused_fwd("pRotatE", ent, rel, gamma, sample, neg, w, mode, modulus=mod)
+    _close(f["pos"], pos)
+    _close(f["neg"], ngs)
+    assert abs(f["stats"][3] - loss) <= 1e-5 * abs(loss)
+    _close(H.score("pRotatE", ent, rel, gamma, sample, modulus=mod), pos)
+    _close(H.score("pRotatE", ent, rel, gamma, sample, neg, mode, modulus=mod), ngs)
+    g_ent, g_rel = H.fused_bwd("pRotatE", ent, rel, gamma, sample, neg, mode, f, modulus=mod)
+    _grad_close(g_ent, ge)
+    _grad_close(g_rel, gr)
+    assert abs(H.modulus_grad(f, gamma, mod) - gm) <= 1e-4 * abs(gm)
+    # unfused backward with arbitrary upstream gradients
+    rng = np.random.RandomState(1)
+    gsc = rng.normal(size=(B, K)).astype(np.float32)
+    ge2, gr2 = np.zeros_like(ent), np.zeros_like(rel)
+    tb = H.tables("pRotatE", ent, rel, gamma, modulus=mod)
+    H.ok(l.kge_score_bwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(gsc), H.P(ge2), H.P(gr2), None))
+    re_, rr_, rm_ = ko.score_grads("pRotatE", ent, rel, sample, neg, mode, gsc, gamma=gamma, modulus=mod)
+    _grad_close(ge2, re_)
+    _grad_close(gr2, rr_)
+    out = np.zeros(1, np.float32)
+    H.ok(l.kge_modulus_grad(H.P(f["neg"]), H.P(gsc), gsc.size, None, None, gamma, H.P(tb._mod), H.P(out), None))
+    assert abs(out[0] - rm_) <= 1e-4 * abs(rm_)
+    if D % 4 == 0:  # sharded instantiations
+        shards = H.split_rows(ent, 3)
+        grads = [np.zeros_like(s) for s in shards]
+        st = H.shards_struct(shards, grads)
+        f1 = H.fused_fwd("pRotatE", ent, rel, gamma, sample, neg, w, mode, shards=st, modulus=mod)
+        for k in f:
+            assert np.array_equal(f[k], f1[k]), k
+        _, gr1 = H.fused_bwd("pRotatE", ent, rel, gamma, sample, neg, mode, f1, shards=st, modulus=mod)
+        _grad_close(H.merge_rows(grads, Nn), g_ent.astype(np.float64), rel=1e-6)
+    # a model enum without its modulus pointer is rejected
+    bad = H.tables("pRotatE", ent, rel, gamma)
+    assert l.kge_score_fwd(C.byref(bad), 0, H.P(sample), B, None, 0, H.P(np.zeros((B, 1), np.float32)), None) == -1
+
+
+def test_protate_ranks_vs_oracle():
+    l = H.lib()
+    rng = np.random.RandomState(4)
+    Nn, R, D, gamma, mod = 70, 3, 12, 9.0, 0.41
+    ent, rel = ko.init_tables("pRotatE", Nn, R, D, gamma, seed=2)
+    ent *= 4.0
+    tri = np.unique(np.stack([rng.randint(Nn, size=400), rng.randint(R, size=400), rng.randint(Nn, size=400)], 1), axis=0)
+    hc, tc = ko.build_filter_csr(tri, Nn, "head"), ko.build_filter_csr(tri, Nn, "tail")
+    queries = np.ascontiguousarray(tri[:70], np.int64)
+    tb = H.tables("pRotatE", ent, rel, gamma, modulus=mod)
+    for mode in MODES:
+        fs = H.csr_struct(hc if mode == "head-batch" else tc)
+        Q = queries.shape[0]
+        ranks = np.zeros(Q, np.int64)
+        ws = np.zeros(l.kge_rank_workspace_bytes(C.byref(tb), Q) + 64, np.uint8)
+        H.ok(l.kge_rank_all(C.byref(tb), H.mode_id(mode), H.P(queries), Q, C.byref(fs), H.P(ranks), None, H.P(ws), None))
+        ref, contested = ko.rank_all("pRotatE", ent, rel, queries, mode, hc, tc, gamma=gamma, tie_margin=2e-5, modulus=mod)
+        assert np.all(np.abs(ranks - ref) <= contested), (ranks, ref)
+        assert (ranks == ref).mean() >= 0.95

@@ -119,3 +119,105 @@ def test_topk_rows_equals_stable_argsort_full_size(rows, cols, k):
     assert torch.equal(ops.topk_rows(x[0], k)[0], ref[0])
     with pytest.raises(ops.N.KgeError):
         ops.topk_rows(x, cols + 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# pRotatE (mkb/models/protate.py) on the shared kernel template
+# --------------------------------------------------------------------------------------------------
+def _protate(g, k, D):
+    entities = {f"e{i}": i for i in range(N_ENT)}
+    relations = {f"r{i}": i for i in range(N_REL)}
+    m = models.pRotatE(hidden_dim=D, entities=entities, relations=relations, gamma=9.0)
+    m._set_params(torch.from_numpy(g[f"{k}/ent"].copy()), torch.from_numpy(g[f"{k}/rel"].copy()),
+                  modulus=torch.from_numpy(g[f"{k}/modulus"].copy()))
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("fused", (False, True))
+@pytest.mark.parametrize("D", (8, 5))
+@pytest.mark.parametrize("mode", ("tail-batch", "head-batch"))
+def test_protate_matches_reference(g, D, mode, fused):
+    k = f"pRotatE_D{D}_{mode}"
+    m = _protate(g, k, D)
+    s = torch.from_numpy(g[f"{k}/sample"]).to(DEV)
+    n = torch.from_numpy(g[f"{k}/neg"]).to(DEV)
+    w = torch.from_numpy(g[f"{k}/weight"]).to(DEV)
+    if fused:
+        loss, ps, ns = ops.fused_adversarial_step(m.spec, m.entity_embedding, m.relation_embedding, s, n, w, mode, 0.5,
+                                                  return_scores=True, modulus=m.modulus)
+    else:
+        ps, ns = m(s), m(s, n, mode)
+        loss = losses.Adversarial(alpha=0.5)(ps, ns, w)
+    for got, name in ((ps, "pos"), (ns, "neg_score")):
+        ref = g[f"{k}/f32/{name}"]
+        assert np.all(np.abs(got.detach().cpu().numpy() - ref) <= score_tol(ref))
+        ref = g[f"{k}/f64/{name}"]
+        assert np.all(np.abs(got.detach().cpu().numpy() - ref) <= score_tol(ref))
+    loss.backward()
+    ref = float(g[f"{k}/f64/loss"])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    for p, name in ((m.entity_embedding, "grad_ent"), (m.relation_embedding, "grad_rel"), (m.modulus, "grad_modulus")):
+        ref = g[f"{k}/f64/{name}"]
+        assert p.grad is not None and p.grad.shape == ref.shape
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max(), name
+    s3 = m(torch.stack([s[:4], s[2:6]]))
+    ref = g[f"{k}/f32/score3d"]
+    assert s3.shape == ref.shape and np.all(np.abs(s3.detach().cpu().numpy() - ref) <= score_tol(ref))
+
+
+def test_protate_device_trainer_and_ranks():
+    """DeviceTrainer (sampler -> fused fwd -> fused bwd -> modulus grad -> Adam on tables AND modulus)
+    tracks the autograd + DenseAdam route; filtered ranks match the oracle."""
+    from mkb_b200 import optim, sampling
+    from mkb_b200.compose import DeviceTrainer
+    from oracle import kge_oracle as ko
+
+    Nn, R, D, B, K, gamma = 300, 5, 32, 24, 16, 9.0
+    rng = np.random.RandomState(0)
+    tri = np.unique(np.stack([rng.randint(Nn, size=3000), rng.randint(R, size=3000), rng.randint(Nn, size=3000)], 1), axis=0)
+    w_all = torch.from_numpy(rng.uniform(0.1, 0.5, len(tri)).astype(np.float32)).to(DEV)
+    T = torch.from_numpy(tri).to(DEV)
+    runs = []
+    for device_loop in (True, False):
+        torch.manual_seed(2)
+        m = models.pRotatE(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                           gamma=gamma).to(DEV)
+        with torch.no_grad():
+            m.entity_embedding.mul_(3.0)
+        ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=range(Nn), relations=range(R), seed=7)
+        if device_loop:
+            tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B)
+        else:
+            opt = optim.DenseAdam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+        for step in range(5):
+            idx = torch.arange(step * B, (step + 1) * B, device=DEV)
+            mode = "head-batch" if step % 2 == 0 else "tail-batch"
+            if device_loop:
+                tr.step(T[idx], w_all[idx], mode)
+                last = tr.loss()
+            else:
+                neg = ns.generate(T[idx], mode)
+                loss = ops.fused_adversarial_step(m.spec, m.entity_embedding, m.relation_embedding, T[idx], neg,
+                                                  w_all[idx], mode, 0.5, modulus=m.modulus)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                last = loss.item()
+        runs.append((m, last))
+    (m0, l0), (m1, l1) = runs
+    assert abs(l0 - l1) <= 1e-4 * abs(l1)
+    assert abs(m0.modulus.item() - m1.modulus.item()) <= 1e-5
+    assert m0.modulus.item() != pytest.approx(0.5 * m0.embedding_range.item(), abs=1e-6)  # it trained
+    upd = (m1.entity_embedding - m0.entity_embedding).abs()
+    assert (upd > 3e-4).float().mean().item() < 1e-3
+    # ranks
+    ev = evaluation.Evaluation(entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)}, batch_size=8,
+                               true_triples=[tuple(map(int, r)) for r in tri])
+    q = [tuple(map(int, r)) for r in tri[:60]]
+    hc, tc = ko.build_filter_csr(tri, Nn, "head"), ko.build_filter_csr(tri, Nn, "tail")
+    ent, rel = m0.entity_embedding.detach().cpu().numpy(), m0.relation_embedding.detach().cpu().numpy()
+    for mode in ("head-batch", "tail-batch"):
+        ref, contested = ko.rank_all("pRotatE", ent, rel, np.array(q), mode, hc, tc, gamma=gamma, tie_margin=2e-5,
+                                     modulus=m0.modulus.item())
+        got = ev.ranks(m0, q, mode).cpu().numpy()
+        assert np.all(np.abs(got - ref) <= contested), (got, ref)

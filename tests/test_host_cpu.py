@@ -25,12 +25,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
-    assert lib.kge_abi_version() == 1
+    assert lib.kge_abi_version() == _native.ABI_VERSION == 2
     assert b"NULL" in lib.kge_strerror(-1)
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_native.KgeTables) == 48
+    assert ctypes.sizeof(_native.KgeTables) == 56 and _native.KgeTables.modulus.offset == 48
     assert ctypes.sizeof(_native.KgeFilterCsr) == 32
     assert _native.KgeTables.hidden_dim.offset == 32 and _native.KgeTables.gamma.offset == 40
 

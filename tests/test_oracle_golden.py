@@ -236,3 +236,30 @@ def test_eval_doctest_replay(eval_doctest):
         for m in ("head-batch", "tail-batch")])
     m = ko.rank_metrics(ranks)
     assert [m[k] for k in ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")] == list(g["doc_metrics"])
+
+
+@pytest.mark.parametrize("D", (8, 5))
+@pytest.mark.parametrize("mode", MODES)
+def test_protate_oracle_matches_reference(D, mode):
+    """pRotatE (mkb/models/protate.py:74-93): scores, loss, table gradients and the
+    gradient of the trainable modulus against the reference executed in fp64 and fp32."""
+    from conftest import load_golden
+
+    g = load_golden("next_rows.npz")
+    k = f"pRotatE_D{D}_{mode}"
+    ent, rel, mod = g[f"{k}/ent"], g[f"{k}/rel"], float(g[f"{k}/modulus"][0, 0])
+    sample, neg, w = g[f"{k}/sample"], g[f"{k}/neg"], g[f"{k}/weight"]
+    assert mod == ko.default_modulus(9.0, D)
+    loss, pos, ngs, ge, gr, gm = ko.train_step("pRotatE", ent, rel, sample, neg, mode, w, gamma=9.0, modulus=mod)
+    np.testing.assert_allclose(pos, g[f"{k}/f64/pos"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ngs, g[f"{k}/f64/neg_score"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(loss, g[f"{k}/f64/loss"], rtol=1e-12)
+    np.testing.assert_allclose(ge, g[f"{k}/f64/grad_ent"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(gr, g[f"{k}/f64/grad_rel"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(gm, float(g[f"{k}/f64/grad_modulus"][0, 0]), rtol=1e-10)
+    assert np.all(np.abs(pos - g[f"{k}/f32/pos"]) <= score_tol(pos))
+    assert np.all(np.abs(ngs - g[f"{k}/f32/neg_score"]) <= score_tol(ngs))
+    assert np.all(np.abs(ge - g[f"{k}/f32/grad_ent"]) <= 1e-4 * np.abs(ge).max())
+    assert abs(gm - float(g[f"{k}/f32/grad_modulus"][0, 0])) <= 1e-4 * abs(gm)
+    s3 = ko.score("pRotatE", ent, rel, np.stack([sample[:4], sample[2:6]]), gamma=9.0, modulus=mod)
+    assert np.all(np.abs(s3 - g[f"{k}/f32/score3d"]) <= score_tol(s3))
