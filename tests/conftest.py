@@ -10,6 +10,16 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# Developer aid (tests/emu/torch_shim.py): KGE_TEST_EMU=1 runs the `-m gpu` files on the CPU emulation of the
+# kernels in a container without a GPU.  Never set by the driver; the real GPU run uses DEV = "cuda".
+EMU = os.environ.get("KGE_TEST_EMU") == "1"
+DEV = "cpu" if EMU else "cuda"
+if EMU:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import torch_shim
+
+    torch_shim.install()
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

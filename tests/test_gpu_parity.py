@@ -14,7 +14,7 @@ if torch.cuda.is_available():
     import mkb_b200
     from mkb_b200 import evaluation, losses, models, ops, optim, sampling
 
-DEV = "cuda"
+from conftest import DEV  # "cuda" (or "cpu" under the KGE_TEST_EMU developer shim)
 
 
 def _model(name, ent, rel, gamma):

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 if torch.cuda.is_available():
     from mkb_b200 import evaluation, losses, models, ops, utils
 
-DEV = "cuda"
+from conftest import DEV  # "cuda" (or "cpu" under the KGE_TEST_EMU developer shim)
 N_ENT, N_REL = 40, 4
 KEYS = ("MRR", "MR", "HITS@1", "HITS@3", "HITS@10")
 
@@ -64,7 +64,7 @@ def test_detail_eval_matches_reference_frame(g, model):
     got = frame.to_numpy(dtype=np.float64)
     assert got.shape == ref.shape
     # MR columns are means of integer ranks over a handful of queries: one contested rank moves them by < 1
-    np.testing.assert_allclose(got, ref, atol=2e-3 + 0.02 * np.abs(ref))
+    assert np.all(np.abs(got - ref) <= 2e-3 + 0.02 * np.abs(ref)), (got, ref)
 
 
 @pytest.mark.parametrize("model", MODELS)

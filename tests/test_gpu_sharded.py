@@ -22,7 +22,7 @@ if torch.cuda.is_available():
     from mkb_b200 import models, ops, sampling
     from mkb_b200.compose import DeviceTrainer
 
-DEV = "cuda"
+from conftest import DEV  # "cuda" (or "cpu" under the KGE_TEST_EMU developer shim)
 
 
 def _problem(model, Nn, R, D, B, K, seed, gamma=9.0):
