@@ -258,6 +258,17 @@ int kge_rank_all(const kge_tables_t* tables, int mode, const int64_t* queries, i
                  const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out, void* workspace,
                  kge_stream_t stream);
 
+/* K5 over ONE shard of a row-sharded table ("shard candidates by owner, each GPU counts
+ * #{e in shard: s_e > s_pos}, all-reduce of the counts"): counts[q] = number of unfiltered entities of
+ * shard `shard_index` that outrank query q's positive (ties by entity id as in kge_rank_all), so that
+ * rank[q] = 1 + sum over shards of counts[q].  The query's own two rows (fixed side, positive) are
+ * read through the shard table wherever they live, and every rank computes the positive's score with
+ * the same instruction sequence, so no broadcast of it is needed.  fp32 tile kernel for all models.
+ * scores_out (optional) is the FULL [Q, n_entity] matrix; only this shard's columns are written. */
+int kge_rank_counts_sharded(const kge_tables_t* tables, const kge_shards_t* shards, int32_t shard_index,
+                            int mode, const int64_t* queries, int64_t Q, const kge_filter_csr_t* filter,
+                            int64_t* counts, float* scores_out, void* workspace, kge_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K8  exact top-k of every row of a score matrix.  Replaces the argsort-then-slice of
  *     utils.TopK._get_rank (mkb/utils/top_k.py:226-234) and of the distillation loop's top-k negative

@@ -89,6 +89,8 @@ PROTOTYPES = {
                                         _P, _P, _P, _P, _P, _P]),
     "kge_score_fwd_sharded": (C.c_int, [C.POINTER(KgeTables), C.POINTER(KgeShards), C.c_int, _P, _I64, _P, _I64,
                                         _P, _P]),
+    "kge_rank_counts_sharded": (C.c_int, [C.POINTER(KgeTables), C.POINTER(KgeShards), C.c_int32, C.c_int, _P, _I64,
+                                          C.POINTER(KgeFilterCsr), _P, _P, _P, _P]),
     "kge_sample_negatives": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64,
                                        C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]),
     "kge_filter_pool": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,

@@ -286,6 +286,27 @@ class DeviceTrainer:
         else:
             ops.merge_rows(self.ent_shards, self.n_entity, out=full)
 
+    def sharded_ranks(self, evaluation, dataset, mode):
+        """Filtered ranks of ``dataset``'s queries straight from the row shards — no gathered table
+        (SURVEY §8(e)): every rank counts the entities of ITS shard that outrank each positive
+        (`kge_rank_counts_sharded`), one all-reduce sums the counts.  Same ranks on every rank."""
+        import numpy as np
+
+        if self.mode != "rowshard":
+            raise RuntimeError("sharded_ranks needs mode='rowshard'")
+        queries = torch.as_tensor(np.asarray(dataset, dtype=np.int64).reshape(-1, 3)).to(self.dev)
+        csr = evaluation._filter("head" if mode == "head-batch" else "tail", self.dev)
+        mine = [self.rank] if self.distributed else range(self.n_shards)
+        counts = torch.zeros(queries.shape[0], dtype=torch.int64, device=self.dev)
+        chunk = max(int(evaluation.batch_size), 1) * 64
+        for lo in range(0, queries.shape[0], chunk):
+            for s_idx in mine:
+                counts[lo:lo + chunk] += ops.rank_counts_sharded(self.spec, self.shards, s_idx, self.n_entity,
+                                                                 self.rel, queries[lo:lo + chunk], mode, csr)
+        if self.distributed:
+            torch.distributed.all_reduce(counts, group=self.group)
+        return counts + 1
+
     def _step_rowshard(self, sample, weight, B, mode, h):
         neg, coef_pos, coef_neg = self.neg[:B], self.coef_pos[:B], self.coef_neg[:B]
         if h:

@@ -55,7 +55,18 @@ struct RankParams {
   int ent_stride, rel_stride;
   float gamma, phase_div;
   const float* modulus;  // pRotatE: device scalar (else null)
+  // K7 (row-sharded table): `ent` / `N` describe ONE shard; local row l is entity l * id_mul + id_add.
+  // The two rows a query itself needs (fixed side, positive) may live on other shards: `shard`.
+  int64_t id_mul, id_add, n_global;
+  const float* shard[KGE_MAX_SHARDS];
+  unsigned n_shards;  // 0: unsharded
 };
+
+__device__ __forceinline__ const float* rk_entity_row(const RankParams& p, int64_t id) {
+  if (p.n_shards == 0) return p.ent + id * (int64_t)p.ent_stride;
+  const unsigned u = (unsigned)id, q = u / p.n_shards;
+  return p.shard[u - q * p.n_shards] + (int64_t)q * p.ent_stride;
+}
 
 template <int M>
 __device__ __forceinline__ float rk_modulus(const RankParams& p) {
@@ -89,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
   using T = Traits<M>;
   const int qi = blockIdx.x;
   const int64_t h = p.queries[3 * qi], r = p.queries[3 * qi + 1], t = p.queries[3 * qi + 2];
-  const float* fixed = p.ent + (HEAD ? t : h) * (int64_t)p.ent_stride;
+  const float* fixed = rk_entity_row(p, HEAD ? t : h);
   const float* relrow = p.rel + r * (int64_t)p.rel_stride;
   float* q = p.qmat + (int64_t)qi * p.ent_stride;
   for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
@@ -102,15 +113,15 @@ __global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const float* e = p.ent + (HEAD ? h : t) * (int64_t)p.ent_stride;
+    const float* e = rk_entity_row(p, HEAD ? h : t);
     float acc = 0.f;
     for (int d = 0; d < p.D; ++d)
       acc = cand_acc<M>(acc, q[d], T::NC == 2 ? q[p.D + d] : 0.f, e[d], T::NC == 2 ? e[p.D + d] : 0.f, p.phase_div);
     p.pos_score[qi] = finish_score<M>(acc, p.gamma, rk_modulus<M>(p));
-    p.ranks[qi] = 1ull;
+    p.ranks[qi] = p.n_shards ? 0ull : 1ull;  // sharded: this shard's COUNT, the caller sums and adds 1
     int64_t lo = 0, hi = 0;
     if (p.has_filter) {
-      const int64_t k = rk_find_key(p.filter.keys, p.filter.n_keys, r * p.N + (HEAD ? t : h));
+      const int64_t k = rk_find_key(p.filter.keys, p.filter.n_keys, r * p.n_global + (HEAD ? t : h));
       if (k >= 0) {
         lo = p.filter.offsets[k];
         hi = p.filter.offsets[k + 1];
@@ -183,15 +194,16 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
       const int64_t lo = p.seg[2 * qi], hi = p.seg[2 * qi + 1];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const int64_t e = e_base + tx * 4 + b;
-        if (e < p.N) {
+        const int64_t el = e_base + tx * 4 + b;  // row of this shard (= entity id when unsharded)
+        if (el < p.N) {
+          const int64_t e = el * p.id_mul + p.id_add;
           const float s = finish_score<M>(acc[a][b], p.gamma, rk_modulus<M>(p));
           const bool beats = (s > sp) || (s == sp && e < pos);
           bool filtered = false;
           if ((beats || p.scores_out) && e != pos && hi > lo)
             filtered = rk_member(p.filter.members, lo, hi, e);
           if (beats && e != pos && !filtered) ++cnt;
-          if (p.scores_out) p.scores_out[(int64_t)qi * p.N + e] = filtered ? sp + (-1e5f) : s;
+          if (p.scores_out) p.scores_out[(int64_t)qi * p.n_global + e] = filtered ? sp + (-1e5f) : s;
         }
       }
     }
@@ -217,22 +229,40 @@ extern "C" size_t kge_rank_workspace_bytes(const kge_tables_t* t, int64_t Q) {
   return (size_t)Q * (row * sizeof(float) + sizeof(float) + 2 * sizeof(int64_t)) + 64;
 }
 
-extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* queries, int64_t Q,
-                            const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out,
-                            void* workspace, kge_stream_t stream) {
-  if (!t || !t->entity || !t->relation || !queries || !ranks || !workspace) return KGE_E_NULL;
+static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_index, int mode, const int64_t* queries,
+                    int64_t Q, const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out, void* workspace,
+                    kge_stream_t stream) {
+  if (!t || !t->relation || !queries || !ranks || !workspace) return KGE_E_NULL;
+  if (!sh && !t->entity) return KGE_E_NULL;
   if (t->model < KGE_TRANSE || t->model > KGE_PROTATE) return KGE_E_MODEL;
   if (t->model == KGE_PROTATE && !t->modulus) return KGE_E_NULL;
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   if (Q < 0 || Q > INT32_MAX / kTQ || t->hidden_dim <= 0 || t->n_entity <= 0) return KGE_E_SIZE;
-  if (Q == 0) return KGE_OK;
   RankParams p{};
+  p.N = t->n_entity;
+  p.n_global = t->n_entity;
+  p.id_mul = 1;
+  p.id_add = 0;
   p.ent = t->entity;
+  if (sh) {
+    if (sh->n_shards < 1 || sh->n_shards > KGE_MAX_SHARDS || shard_index < 0 || shard_index >= sh->n_shards ||
+        t->n_entity > INT32_MAX)
+      return KGE_E_SIZE;
+    for (int s = 0; s < sh->n_shards; ++s) {
+      if (!sh->entity[s]) return KGE_E_NULL;
+      p.shard[s] = sh->entity[s];
+    }
+    p.n_shards = (unsigned)sh->n_shards;
+    p.id_mul = sh->n_shards;
+    p.id_add = shard_index;
+    p.ent = sh->entity[shard_index];
+    p.N = (t->n_entity - shard_index + sh->n_shards - 1) / sh->n_shards;  // rows of this shard
+  }
+  if (Q == 0) return KGE_OK;
   p.rel = t->relation;
   p.queries = queries;
   p.has_filter = filter && filter->n_keys > 0;
   if (p.has_filter) p.filter = *filter;
-  p.N = t->n_entity;
   p.Q = (int)Q;
   p.D = t->hidden_dim;
   p.ent_stride = t->hidden_dim * entity_comps(t->model);
@@ -251,12 +281,14 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((Q + kTQ - 1) / kTQ), (unsigned)((p.N + kTE - 1) / kTE));
   if (grid.y > 65535) return KGE_E_SIZE;
-  // dot-product models: GEMM on the tensor cores when the shape allows (otherwise the fp32 tiles)
-  const bool dot_model = (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT);
+  // dot-product models: GEMM on the tensor cores when the shape allows (otherwise the fp32 tiles);
+  // the sharded variant keeps to the fp32 tiles (the tcgen05 kernel assumes row == entity id)
+  const bool dot_model = !sh && (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT);
 #define KGE_CASE(MM)                                                                              \
   case MM:                                                                                        \
     if (mode == KGE_HEAD_BATCH) rank_prepare_kernel<MM, true><<<(unsigned)Q, kThreads, 0, st>>>(p); \
     else rank_prepare_kernel<MM, false><<<(unsigned)Q, kThreads, 0, st>>>(p);                     \
+    if (p.N == 0) break; /* a shard without rows (more shards than entities) */                   \
     if (dot_model &&                                                                              \
         rank_tc_launch(p.qmat, p.ent, p.N, p.ent_stride, queries, p.Q, filter, p.has_filter != 0, \
                        p.pos_score, p.seg, p.ranks, scores_out, mode == KGE_HEAD_BATCH, st) == KGE_OK) \
@@ -274,4 +306,17 @@ extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* quer
 #undef KGE_CASE
   KGE_LAUNCH_CHECK();
   return KGE_OK;
+}
+
+extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* queries, int64_t Q,
+                            const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out,
+                            void* workspace, kge_stream_t stream) {
+  return run_rank(t, nullptr, 0, mode, queries, Q, filter, ranks, scores_out, workspace, stream);
+}
+
+extern "C" int kge_rank_counts_sharded(const kge_tables_t* t, const kge_shards_t* shards, int32_t shard_index,
+                                       int mode, const int64_t* queries, int64_t Q, const kge_filter_csr_t* filter,
+                                       int64_t* counts, float* scores_out, void* workspace, kge_stream_t stream) {
+  if (!shards) return KGE_E_NULL;
+  return run_rank(t, shards, shard_index, mode, queries, Q, filter, counts, scores_out, workspace, stream);
 }

@@ -108,13 +108,16 @@ class Evaluation:
     def _update(metrics, ranks):
         return _update(metrics, ranks.tolist())
 
-    def eval(self, model, dataset):
+    def eval(self, model, dataset, ranks_fn=None):
         """MRR, MR, HITS@1/3/10 over head-batch then tail-batch queries, rounded to 4 dp
-        (evaluation.py:185-199)."""
+        (evaluation.py:185-199).  ``ranks_fn(dataset, mode)`` (not in the reference) substitutes another
+        source of ranks, e.g. ``functools.partial(trainer.sharded_ranks, evaluation)`` for a row-sharded
+        table that is never gathered."""
         metrics = _new_metrics()
         with torch.no_grad():
             for mode in ("head-batch", "tail-batch"):
-                metrics = self._update(metrics, self.ranks(model, dataset, mode))
+                ranks = self.ranks(model, dataset, mode) if ranks_fn is None else ranks_fn(dataset, mode)
+                metrics = self._update(metrics, ranks)
         return {name: round(metric.get(), 4) for name, metric in metrics.items()}
 
     def eval_relations(self, model, dataset):

@@ -535,6 +535,30 @@ def score_sharded(spec, shards, n_entity, rel, sample, neg=None, mode=None):
     return out
 
 
+def rank_counts_sharded(spec, shards, shard_index, n_entity, rel, queries, mode, csr=None, modulus=None):
+    """int64 ``[Q]``: how many unfiltered entities of shard ``shard_index`` outrank each query's positive
+    (kge_rank_counts_sharded).  ``rank = 1 + sum over shards``."""
+    lib = N.load()
+    N.require_cuda(rel, queries)
+    rel = rel.detach().contiguous()
+    queries = _prep_ids(queries, rel.device)
+    Q = queries.shape[0]
+    dev = rel.device
+    counts = torch.zeros(Q, dtype=torch.int64, device=dev)
+    tb = spec.struct_sharded(n_entity, rel, modulus.detach() if modulus is not None else None)
+    full = N.KgeTables(None, rel.data_ptr(), int(n_entity), rel.shape[0], spec.hidden_dim, spec.model_id, spec.gamma,
+                       spec.embedding_range, None)
+    ws = torch.empty(max(lib.kge_rank_workspace_bytes(C.byref(full), Q), 8), dtype=torch.uint8, device=dev)
+    fs = csr.to(dev).struct() if csr is not None else None
+    with torch.cuda.device(dev):
+        N.check(lib.kge_rank_counts_sharded(C.byref(tb), C.byref(shards.struct()), int(shard_index), _mode_id(mode),
+                                            N.ptr(queries), Q, C.byref(fs) if fs is not None else None,
+                                            N.ptr(counts), None, N.ptr(ws), N.stream_ptr(dev)),
+                "kge_rank_counts_sharded")
+    N.count_launch(2)
+    return counts
+
+
 # ---------------------------------------------------------------------------------------------
 # K4 sampler
 # ---------------------------------------------------------------------------------------------

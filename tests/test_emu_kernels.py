@@ -409,3 +409,45 @@ def test_protate_ranks_vs_oracle():
         ref, contested = ko.rank_all("pRotatE", ent, rel, queries, mode, hc, tc, gamma=gamma, tie_margin=2e-5, modulus=mod)
         assert np.all(np.abs(ranks - ref) <= contested), (ranks, ref)
         assert (ranks == ref).mean() >= 0.95
+
+
+@pytest.mark.parametrize("model", MODELS + ("pRotatE",))
+@pytest.mark.parametrize("G", (1, 3, 16))
+def test_sharded_rank_counts_sum_to_unsharded_ranks(model, G):
+    """K5 over row shards: 1 + sum of the per-shard counts == kge_rank_all on the whole table."""
+    l = H.lib()
+    rng = np.random.RandomState(G)
+    Nn, R, D, gamma, mod = 75, 3, 8, 9.0, 0.4
+    ent, rel = ko.init_tables(model, Nn, R, D, gamma, seed=G)
+    ent *= 4.0
+    ent[5] = ent[9]  # exact ties, resolved by entity id across shard boundaries
+    ent[17] = ent[9]
+    tri = np.unique(np.stack([rng.randint(Nn, size=300), rng.randint(R, size=300), rng.randint(Nn, size=300)], 1), axis=0)
+    hc, tc = ko.build_filter_csr(tri, Nn, "head"), ko.build_filter_csr(tri, Nn, "tail")
+    queries = np.ascontiguousarray(np.concatenate([tri[:40], [[9, 0, 9], [5, 1, 17]]]), np.int64)
+    Q = queries.shape[0]
+    mk = dict(modulus=mod) if model == "pRotatE" else {}
+    tb = H.tables(model, ent, rel, gamma, **mk)
+    shards = H.split_rows(ent, G)
+    st = H.shards_struct(shards)
+    for mode in MODES:
+        fs = H.csr_struct(hc if mode == "head-batch" else tc)
+        ws = np.zeros(l.kge_rank_workspace_bytes(C.byref(tb), Q) + 64, np.uint8)
+        full = np.zeros(Q, np.int64)
+        sc_full = np.full((Q, Nn), np.nan, np.float32)
+        H.ok(l.kge_rank_all(C.byref(tb), H.mode_id(mode), H.P(queries), Q, C.byref(fs), H.P(full), H.P(sc_full), H.P(ws), None))
+        tbs = H.tables(model, ent, rel, gamma, **mk)
+        tbs.entity = None
+        total = np.ones(Q, np.int64)
+        sc = np.full((Q, Nn), np.nan, np.float32)
+        for s in range(G):
+            counts = np.full(Q, -7, np.int64)
+            H.ok(l.kge_rank_counts_sharded(C.byref(tbs), C.byref(st), s, H.mode_id(mode), H.P(queries), Q, C.byref(fs),
+                                           H.P(counts), H.P(sc), H.P(ws), None))
+            assert counts.min() >= 0
+            total += counts
+        np.testing.assert_array_equal(total, full)
+        np.testing.assert_array_equal(sc, sc_full)
+        ref, contested = ko.rank_all(model, ent, rel, queries, mode, hc, tc, gamma=gamma, tie_margin=2e-5,
+                                     **({"modulus": mod} if model == "pRotatE" else {}))
+        assert np.all(np.abs(total - ref) <= contested)
