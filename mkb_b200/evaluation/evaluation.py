@@ -70,7 +70,12 @@ class Evaluation:
     (evaluation.py:137-146).  ``device`` is where the reference would move each batch; the kernels
     run on the model's CUDA device."""
 
-    def __init__(self, entities, relations, batch_size, true_triples=[], device="cpu", num_workers=1):
+    def __init__(self, entities, relations, batch_size, true_triples=[], device="cpu", num_workers=1,
+                 distributed=False):
+        """``distributed=True`` (not in the reference): under an initialised ``torch.distributed`` group with
+        replicated tables, every rank ranks a contiguous slice of the queries and the ranks are all-gathered
+        back in query order, so every rank reports the same metrics as a single-GPU run."""
+        self.distributed = distributed
         self.entities = entities
         self.relations = relations
         self.true_triples = true_triples
@@ -97,12 +102,35 @@ class Evaluation:
         """int64 ranks (on the model's device) of the true head (head-batch) / tail (tail-batch)."""
         dev = model.entity_embedding.device
         queries = torch.as_tensor(np.asarray(dataset, dtype=np.int64).reshape(-1, 3)).to(dev)
+        if self.distributed and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            return self._ranks_distributed(model, queries, mode)
+        return self._ranks_local(model, queries, mode)
+
+    def _ranks_local(self, model, queries, mode):
+        dev = queries.device
         csr = self._filter("head" if mode == "head-batch" else "tail", dev)
         chunk = max(int(self.batch_size), 1) * 64  # rank tiles are 64 queries; keep launches large
         out = [ops.rank_all(model.spec, model.entity_embedding, model.relation_embedding, queries[lo:lo + chunk],
                             mode, csr, modulus=getattr(model, "kernel_modulus", None))
                for lo in range(0, queries.shape[0], chunk)]
         return torch.cat(out) if out else torch.zeros(0, dtype=torch.int64, device=dev)
+
+    def _ranks_distributed(self, model, queries, mode):
+        """Queries are independent units: rank r takes the r-th contiguous slice (sizes differ by at most
+        one), one all-gather of the padded int64 ranks restores query order on every rank."""
+        dist = torch.distributed
+        world, rank = dist.get_world_size(), dist.get_rank()
+        bounds = np.linspace(0, queries.shape[0], world + 1).round().astype(np.int64)
+        width = int((bounds[1:] - bounds[:-1]).max()) if queries.shape[0] else 0
+        mine = torch.zeros(width, dtype=torch.int64, device=queries.device)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        if hi > lo:
+            mine[: hi - lo] = self._ranks_local(model, queries[lo:hi], mode)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        if width:
+            dist.all_gather(parts, mine)
+        return torch.cat([parts[r][: int(bounds[r + 1] - bounds[r])] for r in range(world)]) if width else mine
 
     @staticmethod
     def _update(metrics, ranks):

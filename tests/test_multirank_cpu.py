@@ -86,3 +86,54 @@ def test_rank_slices_cover_the_order_once():
         for g in range(len(per_rank[0])):
             sizes = [len(per_rank[r][g]) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1 and max(sizes) <= 64
+
+
+def _eval_worker(rank, world, port, out):
+    """Evaluation(distributed=True): slices + all-gather restore query order (gloo; the per-slice ranks
+    come from the oracle instead of the CUDA kernel)."""
+    from mkb_b200 import evaluation
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(0)
+    Nn, R, D = 30, 3, 4
+    ent, rel = ko.init_tables("TransE", Nn, R, D, 6.0, seed=1)
+    tri = np.unique(np.stack([rng.randint(Nn, size=120), rng.randint(R, size=120), rng.randint(Nn, size=120)], 1), axis=0)
+    hc, tc = ko.build_filter_csr(tri, Nn, "head"), ko.build_filter_csr(tri, Nn, "tail")
+    queries = [tuple(map(int, r)) for r in tri[:23]]  # 23 queries over 2 ranks: uneven slices
+
+    class Model:
+        entity_embedding = torch.zeros(1)
+
+    ev = evaluation.Evaluation(entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)}, batch_size=4,
+                               true_triples=[tuple(map(int, r)) for r in tri], distributed=True)
+    seen = []
+
+    def local(model, q, mode):
+        seen.append(q.shape[0])
+        r, _ = ko.rank_all("TransE", ent, rel, q.numpy(), mode, hc, tc, gamma=6.0)
+        return torch.from_numpy(r)
+
+    ev._ranks_local = local
+    got = {mode: ev.ranks(Model(), queries, mode).numpy() for mode in ("head-batch", "tail-batch")}
+    metrics = ev.eval(Model(), queries)
+    if rank == 0:
+        out["ranks"] = got
+        out["metrics"] = metrics
+        out["seen"] = seen
+        out["ref"] = {mode: ko.rank_all("TransE", ent, rel, np.array(queries), mode, hc, tc, gamma=6.0)[0]
+                      for mode in ("head-batch", "tail-batch")}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_evaluation_restores_query_order():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_eval_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for mode in ("head-batch", "tail-batch"):
+        np.testing.assert_array_equal(out["ranks"][mode], out["ref"][mode])
+    assert all(n in (11, 12) for n in out["seen"])  # each rank only ranked its slice
+    both = np.concatenate([out["ref"]["head-batch"], out["ref"]["tail-batch"]])
+    assert out["metrics"] == ko.rank_metrics(both)
