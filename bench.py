@@ -236,7 +236,7 @@ def run_ours(args):
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev)
-    topts = {"mode": args.mode}
+    topts = {"mode": args.mode, "backward": args.backward}
     if args.virtual_shards:
         topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
     trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
@@ -372,7 +372,10 @@ def run_ours(args):
                         f" [{trainer.mode_note}]" if trainer.mode_note else "")),
                 "l2": "working set per step (tables+grads+Adam moments = "
                       f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
-                "step": "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
+                "step": ("sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
+                         if trainer.backward == "scatter" else
+                         "sample_negatives + fused_fwd + by-entity backward (CSR build, queries, dq pass, per-entity "
+                         "gradient + Adam in place) + adam(relation)")
                         if trainer.mode in ("single", "allreduce") else
                         "sample_negatives + fused_fwd_sharded + fused_bwd_sharded + adam(own shard(s)) + adam(relation)"
                         if trainer.mode == "rowshard" else
@@ -381,7 +384,9 @@ def run_ours(args):
                 "final_loss": final_loss,
             },
             "roofline": {
-                "kernel": "score_bwd_kernel (fused backward, K3)", "bound": "hbm", "achieved": bwd_gbs, "peak": hbm,
+                "kernel": "score_bwd_kernel (fused backward, K3)" if trainer.backward == "scatter" else
+                          "by-entity backward incl. the entity table's Adam (byent.cu; bytes still counted as K3's)",
+                "bound": "hbm", "achieved": bwd_gbs, "peak": hbm,
                 "unit": "GB/s", "frac": bwd_gbs / hbm, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bwd_b, "avg_launch_ms": bwd_ms,
                 "also": {"kernel": "score_neg_kernel<FUSED> (fused forward, K2)", "achieved": fwd_gbs,
@@ -418,6 +423,9 @@ def main():
                     help="multi-GPU scheme of DeviceTrainer (default colpar: column-parallel backward + fused "
                          "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce; rowshard: "
                          "entity table row-sharded over the GPUs, P2P row gathers + remote gradient REDs)")
+    ap.add_argument("--backward", default="scatter", choices=["scatter", "by_entity"],
+                    help="single-GPU backward: scatter = K3 vector REDs + dense Adam (default, the measured path); "
+                         "by_entity = atomics-free per-entity backward with Adam fused in (csrc/byent.cu)")
     ap.add_argument("--virtual-shards", type=int, default=0,
                     help="single GPU only: run the row-sharded kernels with this many local shards")
     args = ap.parse_args()

@@ -290,6 +290,28 @@ int kge_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
                   kge_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * By-entity backward with the optimizer fused in (csrc/byent.cu): an atomics-free alternative to
+ * kge_fused_bwd + kge_adam_step for the ENTITY table of the device-resident step — replaces
+ * error.backward(); optimizer.step(); optimizer.zero_grad() (mkb/compose/pipeline.py:236-240).
+ * Same inputs as kge_fused_bwd (K2's coefficients and stats).  The candidate-row gradients are formed
+ * entity by entity from a per-step CSR of (positive, candidate) pairs, summed in a fixed order in
+ * registers, and consumed by torch.optim.Adam's update of that row in place: the entity gradient never
+ * exists in memory.  The relation table is handled the same way (per-positive relation-gradient rows,
+ * summed per relation in index order, Adam in place), so no atomic touches a float anywhere and the step
+ * is bit-reproducible run to run.  entity_table / relation_table must be tables->entity / ->relation
+ * (updated IN PLACE); exp_avg* are their dense moments.
+ * hidden_dim % 4 == 0; step is 1-based; workspace: kge_byent_workspace_bytes(tables, B, K) bytes of
+ * scratch, 16-byte aligned, contents need not be initialised.
+ * ------------------------------------------------------------------------------------------- */
+size_t kge_byent_workspace_bytes(const kge_tables_t* tables, int64_t B, int64_t K);
+int kge_bwd_by_entity_adam(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                           const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
+                           const float* stats, const float* grad_loss, float* entity_table, float* exp_avg,
+                           float* exp_avg_sq, float* relation_table, float* rel_exp_avg, float* rel_exp_avg_sq,
+                           int64_t step, float lr, float beta1, float beta2, float eps, void* workspace,
+                           kge_stream_t stream);
+
 /* Adam on one column chunk: grad_chunk is dense [rows, comps*ncols]; param and the moments keep the
  * table layout (row stride row_stride floats, second component at +im_off, chunk at column col0). */
 int kge_adam_step_chunk(float* param, float* grad_chunk, float* exp_avg, float* exp_avg_sq, int64_t rows,

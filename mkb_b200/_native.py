@@ -77,6 +77,9 @@ PROTOTYPES = {
                                 _P, _P, _P]),
     "kge_fused_bwd_chunk": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, _P, _P, _P,
                                       C.c_int32, C.c_int32, C.c_int32, _I64, _P, _P, _P]),
+    "kge_byent_workspace_bytes": (C.c_size_t, [C.POINTER(KgeTables), _I64, _I64]),
+    "kge_bwd_by_entity_adam": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _P,
+                                         _P, _P, _P, _I64, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P]),
     "kge_adam_step_chunk": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, _I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                       _P]),

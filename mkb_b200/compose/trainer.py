@@ -92,7 +92,7 @@ class DeviceTrainer:
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,
-                 scalar_red=False):
+                 scalar_red=False, backward="scatter"):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -150,6 +150,13 @@ class DeviceTrainer:
         self.t = 0
         self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd] CUDA events (bench.py)
 
+        # single-GPU flow: "scatter" = K3 (vector REDs into a dense gradient) + dense Adam;
+        # "by_entity" = csrc/byent.cu (per-step CSR by entity, no atomics, Adam fused, deterministic)
+        if backward not in ("scatter", "by_entity"):
+            raise ValueError("backward must be 'scatter' or 'by_entity'")
+        self.backward = backward if mode == "single" else "scatter"
+        if self.backward == "by_entity" and D % 4 != 0:
+            raise ValueError("backward='by_entity' needs hidden_dim % 4 == 0")
         if mode == "rowshard":
             self._setup_rowshard(model, f32, scalar_red)
         elif mode == "colpar":
@@ -164,6 +171,8 @@ class DeviceTrainer:
             self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
             self.coef_pos = torch.empty(max_batch, **f32)
             self.coef_neg = torch.empty((max_batch, K), **f32)
+            if self.backward == "by_entity":
+                self._byent_ws = ops.byent_workspace(self.spec, self.ent, self.rel, max_batch, K, self.modulus)
 
     # ------------------------------------------------------------------------------------------
     # colpar set-up
@@ -379,8 +388,13 @@ class DeviceTrainer:
             return self._step_colpar(sample, B, mode, h)
         if h:
             h[2].record()
-        ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
-                               self.g_ent, self.g_rel, modulus=mod)
+        if self.backward == "by_entity":
+            ops.bwd_by_entity_adam_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
+                                       self.m_ent, self.v_ent, self.m_rel, self.v_rel, self.t, self.lr, b1, b2,
+                                       self.eps, self._byent_ws, modulus=mod)
+        else:
+            ops.fused_backward_raw(self.spec, self.ent, self.rel, sample, neg, mode, coef_pos, coef_neg, self.stats,
+                                   self.g_ent, self.g_rel, modulus=mod)
         if h:
             h[3].record()
         if mod is not None:
@@ -389,8 +403,11 @@ class DeviceTrainer:
             ops.adam_step(mod, self.g_mod, self.m_mod, self.v_mod, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
         if self.distributed:
             parallel.allreduce_gradients(self._gflat, self.group)
-        ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
-        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        if self.backward != "by_entity":  # by_entity already applied Adam to both tables
+            ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps,
+                          zero_grad=True)
+            ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps,
+                          zero_grad=True)
         return self.stats
 
     def _step_colpar(self, sample, B, mode, h):

@@ -301,6 +301,11 @@ struct BwdParams {
   float* gshard[KGE_MAX_SHARDS];
   unsigned n_shards;
   int scalar_red;
+  // by-entity backward (byent.cu), pass 1: per-positive gradient rows of the head / tail [B, NC*D] and of
+  // the relation [B, RC*D]
+  float* gh_buf;
+  float* gt_buf;
+  float* gr_buf;
 };
 
 // Gradient row of an entity from a split id: in the owner's (possibly remote) gradient shard.
@@ -321,7 +326,10 @@ __device__ __forceinline__ void red_row(const BwdParams& p, float* dst, const fl
 
 constexpr int kTileK = 256;
 
-template <int M, bool HEAD, int VEC, bool SHARD = false>
+// DQONLY (pass 1 of the by-entity backward, byent.cu): the candidates' row gradients are NOT scattered —
+// pass 2 forms them entity by entity without atomics — and the head / tail gradient rows of each positive
+// are stored to per-positive buffers instead of being added into the gradient table.
+template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false>
 __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   using T = Traits<M>;
   extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC]
@@ -416,8 +424,10 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
               for (int v = 0; v < VEC; ++v)
                 cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
                             dq0[v], dq1[v], p.phase_div);
-              red_row<VEC, SHARD>(p, grow + d, g0);
-              if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
+              if constexpr (!DQONLY) {
+                red_row<VEC, SHARD>(p, grow + d, g0);
+                if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
+              }
             }
           }
         }
@@ -503,6 +513,25 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
           gh1[v] = da1;
         }
         rel_bwd<M>(dr0, dr1, r0[v], r1[v], p.phase_div, gr0[v], gr1[v]);
+      }
+      if constexpr (DQONLY) {
+        float* bh = p.gh_buf + (int64_t)blockIdx.x * p.g_ent_stride;
+        float* bt = p.gt_buf + (int64_t)blockIdx.x * p.g_ent_stride;
+        if constexpr (VEC == 4) {
+          *reinterpret_cast<float4*>(bh + d) = make_float4(gh0[0], gh0[1], gh0[2], gh0[3]);
+          *reinterpret_cast<float4*>(bt + d) = make_float4(gt0[0], gt0[1], gt0[2], gt0[3]);
+          if constexpr (T::NC == 2) {
+            *reinterpret_cast<float4*>(bh + p.g_im_off + d) = make_float4(gh1[0], gh1[1], gh1[2], gh1[3]);
+            *reinterpret_cast<float4*>(bt + p.g_im_off + d) = make_float4(gt1[0], gt1[1], gt1[2], gt1[3]);
+          }
+        }
+        float* br = p.gr_buf + (int64_t)blockIdx.x * p.g_rel_stride;
+        if constexpr (VEC == 4) {
+          *reinterpret_cast<float4*>(br + d) = make_float4(gr0[0], gr0[1], gr0[2], gr0[3]);
+          if constexpr (T::RC == 2)
+            *reinterpret_cast<float4*>(br + p.g_im_off + d) = make_float4(gr1[0], gr1[1], gr1[2], gr1[3]);
+        }
+        continue;
       }
       float* gh = grad_row<SHARD>(p, hid);
       float* gt = grad_row<SHARD>(p, tidx);
@@ -638,9 +667,9 @@ static void fill_fwd(FwdParams& p, const kge_tables_t* t, const kge_shards_t* sh
   p.modulus = t->modulus;
 }
 
-template <int M, bool HEAD, int VEC, bool SHARD = false>
+template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false>
 static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = score_bwd_kernel<M, HEAD, VEC, SHARD>;
+  auto kern = score_bwd_kernel<M, HEAD, VEC, SHARD, DQONLY>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, st>>>(p);
@@ -655,8 +684,11 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
                    int64_t K, const float* gpos, const float* gneg, const float* stats,
                    const float* grad_loss, float* grad_ent, float* grad_rel, cudaStream_t st,
                    int col0 = 0, int ncols = 0, int n_records = 1, long long record_stride = 0,
-                   const kge_shards_t* sh = nullptr) {
+                   const kge_shards_t* sh = nullptr, float* gh_buf = nullptr, float* gt_buf = nullptr) {
   BwdParams p{};
+  p.gh_buf = gh_buf;
+  p.gt_buf = gt_buf;
+  p.gr_buf = grad_rel;  // pass 1 of the by-entity backward stores per-positive relation rows there
   if (sh) {  // K7: grad_ent is unused, rows resolve through the shard tables
     for (int s = 0; s < sh->n_shards; ++s) {
       p.shard[s] = sh->entity[s];
@@ -719,10 +751,27 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
     ks = want < 1 ? 1 : (want > maxks ? maxks : want);
     if (const char* e = getenv("KGE_KS")) ks = atoi(e) > 0 ? atoi(e) : ks;
   }
+  if (gh_buf) ks = 1;  // pass 1 of the by-entity backward keeps a positive's whole dq in one CTA
   p.k_per_cta = p.K > 0 ? (p.K + ks - 1) / ks : 0;
   if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
   dim3 grid((unsigned)total, (unsigned)ks);
   const size_t smem = (size_t)(G - 1) * entity_comps(t->model) * tpg * VEC * sizeof(float);
+  if (gh_buf) {
+    if (!vec || !gt_buf || !gpos || !aligned16(gh_buf) || !aligned16(gt_buf)) return KGE_E_UNSUPPORTED;
+#define KGE_CASE(MM)                                                                               \
+  case MM:                                                                                         \
+    return mode == KGE_HEAD_BATCH ? launch_bwd<MM, true, 4, false, true>(p, grid, smem, st)        \
+                                  : launch_bwd<MM, false, 4, false, true>(p, grid, smem, st);
+    switch (t->model) {
+      KGE_CASE(KGE_TRANSE)
+      KGE_CASE(KGE_DISTMULT)
+      KGE_CASE(KGE_COMPLEX)
+      KGE_CASE(KGE_ROTATE)
+      KGE_CASE(KGE_PROTATE)
+    }
+#undef KGE_CASE
+    return KGE_E_MODEL;
+  }
   if (sh) {
 #define KGE_CASE(MM)                                                                  \
   case MM:                                                                            \
@@ -752,6 +801,15 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   }
 #undef KGE_CASE
   return KGE_E_MODEL;
+}
+
+// pass 1 of the by-entity backward (byent.cu): dq per positive; the gradient rows of its head / tail /
+// relation are STORED into gh_buf / gt_buf [B, NC*D] and gr_buf [B, RC*D] (no atomics anywhere)
+int dq_pass_launch(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B, const int64_t* neg, int64_t K,
+                   const float* coef_pos, const float* coef_neg, const float* stats, const float* grad_loss,
+                   float* gh_buf, float* gt_buf, float* gr_buf, cudaStream_t st) {
+  return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, /*grad_ent=*/gh_buf,
+                 /*grad_rel=*/gr_buf, st, 0, 0, 1, 0, nullptr, gh_buf, gt_buf);
 }
 
 }  // namespace kge

@@ -385,6 +385,29 @@ def fused_backward_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, st
     N.count_launch()
 
 
+def byent_workspace(spec, ent, rel, B, K, modulus=None):
+    """Scratch buffer for ``bwd_by_entity_adam_raw`` (kge_byent_workspace_bytes)."""
+    lib = N.load()
+    tb = spec.struct(ent, rel, modulus)
+    return torch.empty(max(lib.kge_byent_workspace_bytes(C.byref(tb), B, K), 256), dtype=torch.uint8, device=ent.device)
+
+
+def bwd_by_entity_adam_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, exp_avg, exp_avg_sq,
+                           rel_exp_avg, rel_exp_avg_sq, step, lr, beta1, beta2, eps, workspace, grad_loss=None,
+                           modulus=None):
+    """Atomics-free backward with Adam fused in (kge_bwd_by_entity_adam): updates ``ent``, ``rel`` and
+    their moments IN PLACE; bit-reproducible."""
+    lib = N.load()
+    tb = spec.struct(ent, rel, modulus)
+    B, K = neg.shape
+    N.check(lib.kge_bwd_by_entity_adam(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(neg), K, N.ptr(coef_pos),
+                                       N.ptr(coef_neg), N.ptr(stats), N.ptr(grad_loss), N.ptr(ent), N.ptr(exp_avg),
+                                       N.ptr(exp_avg_sq), N.ptr(rel), N.ptr(rel_exp_avg), N.ptr(rel_exp_avg_sq),
+                                       int(step), lr, beta1, beta2, eps, N.ptr(workspace),
+                                       N.stream_ptr(ent.device)), "kge_bwd_by_entity_adam")
+    N.count_launch(7)
+
+
 def fused_backward_chunk_raw(spec, ent, rel, sample, neg, mode, coef_pos, coef_neg, stats, col0, ncols,
                              g_ent_chunk, g_rel_chunk, grad_loss=None, n_records=1, record_stride=0):
     """K3 restricted to hidden-dim columns [col0, col0+ncols): ADDS into the dense chunk buffers.

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mkb_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libkge_emu.so")
-SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu"]
+SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu", "byent.cu"]
 HEADERS = ["kge_common.cuh"]
 
 
@@ -90,10 +90,10 @@ def rewrite_launches(text):
 
 def _split_top(s):
     parts, depth, cur = [], 0, []
-    for c in s:
-        if c in "(<[":
+    for c in s:  # launch configurations hold casts and member accesses (`t->n`), never template arguments
+        if c in "([":
             depth += 1
-        elif c in ")>]":
+        elif c in ")]":
             depth -= 1
         if c == "," and depth == 0:
             parts.append("".join(cur))

@@ -86,6 +86,10 @@ inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
   return cudaSuccess;
 }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  memset(p, v, n);
+  return cudaSuccess;
+}
 
 namespace emu {
 
@@ -251,6 +255,11 @@ template <class T>
 inline T __shfl_down_sync(unsigned, T v, int delta) {
   const int src = emu::S.cur->lane + delta;
   return emu::warp_exchange(v, src < 32 ? src : emu::S.cur->lane);
+}
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int delta) {
+  const int src = emu::S.cur->lane - delta;
+  return emu::warp_exchange(v, src >= 0 ? src : emu::S.cur->lane);
 }
 inline unsigned __ballot_sync(unsigned, int pred) {
   using namespace emu;

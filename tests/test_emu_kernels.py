@@ -451,3 +451,75 @@ def test_sharded_rank_counts_sum_to_unsharded_ranks(model, G):
         ref, contested = ko.rank_all(model, ent, rel, queries, mode, hc, tc, gamma=gamma, tie_margin=2e-5,
                                      **({"modulus": mod} if model == "pRotatE" else {}))
         assert np.all(np.abs(total - ref) <= contested)
+
+
+@pytest.mark.parametrize("model", MODELS + ("pRotatE",))
+@pytest.mark.parametrize("mode", MODES)
+def test_by_entity_backward_with_fused_adam_equals_scatter_plus_adam(model, mode):
+    """kge_bwd_by_entity_adam (per-step CSR by entity, no atomics, Adam in place) == kge_fused_bwd followed
+    by kge_adam_step on the entity table; relation gradient identical; result independent of the
+    scatter order (deterministic)."""
+    l = H.lib()
+    Nn, R, D, B, K, gamma, mod = 37, 3, 24, 9, 14, 9.0, 0.4
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=7)
+    sample[3, 2] = sample[3, 0]  # a positive whose head is also its tail
+    neg[2, :5] = neg[2, 0]       # duplicates inside a row
+    mk = dict(modulus=mod) if model == "pRotatE" else {}
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, **mk)
+    ge, gr = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f, **mk)
+    rng = np.random.RandomState(3)
+    m0 = (np.abs(rng.normal(size=ent.shape)) * 1e-3).astype(np.float32)
+    v0 = (np.abs(rng.normal(size=ent.shape)) * 1e-6).astype(np.float32)
+    p_ref, m_ref, v_ref, g_tmp = ent.copy(), m0.copy(), v0.copy(), ge.copy()
+    H.ok(l.kge_adam_step(H.P(p_ref), H.P(g_tmp), H.P(m_ref), H.P(v_ref), p_ref.size, 4, 1e-3, 0.9, 0.999, 1e-8, 1, None))
+    r_ref, rm_ref, rv_ref, g_tmp = rel.copy(), np.zeros_like(rel), np.zeros_like(rel), gr.copy()
+    H.ok(l.kge_adam_step(H.P(r_ref), H.P(g_tmp), H.P(rm_ref), H.P(rv_ref), r_ref.size, 4, 1e-3, 0.9, 0.999, 1e-8, 1, None))
+    outs = []
+    for trial in range(2):
+        p1, m1, v1 = ent.copy(), m0.copy(), v0.copy()
+        r1, rm1, rv1 = rel.copy(), np.zeros_like(rel), np.zeros_like(rel)
+        tb = H.tables(model, p1, r1, gamma, **mk)
+        ws = np.full(l.kge_byent_workspace_bytes(C.byref(tb), B, K) + 64, 0xAB, np.uint8)  # garbage: must not matter
+        wsp = (ws.ctypes.data + 63) & ~63
+        H.ok(l.kge_bwd_by_entity_adam(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(f["cpos"]),
+                                      H.P(f["cneg"]), H.P(f["stats"]), None, H.P(p1), H.P(m1), H.P(v1), H.P(r1), H.P(rm1),
+                                      H.P(rv1), 4, 1e-3, 0.9, 0.999, 1e-8, wsp, None), "kge_bwd_by_entity_adam")
+        outs.append((p1, m1, v1, r1, rm1, rv1))
+    p1, m1, v1, r1, rm1, rv1 = outs[0]
+    np.testing.assert_allclose(rm1, rm_ref, rtol=1e-4, atol=1e-6 * np.abs(gr).max())
+    assert np.abs((r1 - rel) - (r_ref - rel)).max() <= 2e-3 * np.abs(r_ref - rel).max()
+    # Adam is applied to a gradient that differs only by summation order
+    np.testing.assert_allclose(m1, m_ref, rtol=1e-4, atol=1e-6 * np.abs(ge).max())
+    np.testing.assert_allclose(v1, v_ref, rtol=1e-3, atol=1e-12)
+    upd_ref, upd = p_ref - ent, p1 - ent
+    assert np.abs(upd_ref).max() > 0
+    assert np.abs(upd - upd_ref).max() <= 2e-3 * np.abs(upd_ref).max()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    # wrong table pointer / unsupported dims are rejected before any launch
+    other = ent.copy()
+    tb = H.tables(model, ent, rel, gamma, **mk)
+    assert l.kge_bwd_by_entity_adam(C.byref(tb), 0, H.P(sample), B, H.P(neg), K, H.P(f["cpos"]), H.P(f["cneg"]),
+                                    H.P(f["stats"]), None, H.P(other), H.P(m0), H.P(v0), H.P(rel), H.P(rm1), H.P(rv1), 1,
+                                    1e-3, 0.9, 0.999, 1e-8, wsp, None) == -6
+
+
+def test_by_entity_backward_huge_buckets():
+    """Buckets larger than the in-kernel sort capacity (2048 entries per entity) take the unsorted path."""
+    l = H.lib()
+    model, mode, Nn, R, D, B, K, gamma = "TransE", "tail-batch", 3, 2, 4, 30, 250, 6.0
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=2)
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    ge, gr = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f)
+    p_ref, m_ref, v_ref, g_tmp = ent.copy(), np.zeros_like(ent), np.zeros_like(ent), ge.copy()
+    H.ok(l.kge_adam_step(H.P(p_ref), H.P(g_tmp), H.P(m_ref), H.P(v_ref), p_ref.size, 1, 1e-3, 0.9, 0.999, 1e-8, 1, None))
+    p1, m1, v1 = ent.copy(), np.zeros_like(ent), np.zeros_like(ent)
+    r1, rm1, rv1 = rel.copy(), np.zeros_like(rel), np.zeros_like(rel)
+    tb = H.tables(model, p1, r1, gamma)
+    ws = np.zeros(l.kge_byent_workspace_bytes(C.byref(tb), B, K) + 64, np.uint8)
+    wsp = (ws.ctypes.data + 63) & ~63
+    H.ok(l.kge_bwd_by_entity_adam(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(f["cpos"]), H.P(f["cneg"]),
+                                  H.P(f["stats"]), None, H.P(p1), H.P(m1), H.P(v1), H.P(r1), H.P(rm1), H.P(rv1), 1, 1e-3,
+                                  0.9, 0.999, 1e-8, wsp, None))
+    np.testing.assert_allclose(m1, m_ref, rtol=1e-4, atol=1e-6 * np.abs(ge).max())
+    assert np.abs((p1 - ent) - (p_ref - ent)).max() <= 2e-3 * np.abs(p_ref - ent).max()
