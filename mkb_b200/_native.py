@@ -111,7 +111,13 @@ launches = 0  # number of kernel-launching ABI calls made through this module (b
 
 
 class KgeError(RuntimeError):
-    pass
+    """Raised for every non-zero return of the C ABI; ``code`` is that return value (negative: KGE_E_*,
+    positive: cudaError_t)."""
+
+    code = None
+
+
+E_UNSUPPORTED = -6  # KGE_E_UNSUPPORTED
 
 
 def load(build_if_missing: bool = True):
@@ -142,7 +148,9 @@ def load(build_if_missing: bool = True):
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().kge_strerror(rc).decode()
-        raise KgeError(f"{what or 'kge call'} failed: {msg} (code {rc})")
+        err = KgeError(f"{what or 'kge call'} failed: {msg} (code {rc})")
+        err.code = rc
+        raise err
 
 
 def ptr(t):

@@ -74,6 +74,9 @@ class Pipeline:
                 and isinstance(sampling, NegativeSampling) and len(optimizer.param_groups) == 1
                 and model.entity_embedding.is_cuda):
             return None
+        # the fused forward keeps the query and the K scores of a positive in one CTA's shared memory
+        if (model.entity_dim + 3 + int(sampling.size)) * 4 > 200 * 1024:
+            return None
         params = {id(p) for p in optimizer.param_groups[0]["params"]}
         if not {id(model.entity_embedding), id(model.relation_embedding)} <= params:
             return None
@@ -131,10 +134,15 @@ class Pipeline:
                 weight = data["weight"].to(self.device)
                 negative_sample = sampling.generate(sample=sample, mode=mode).to(self.device)
                 if fuse:
-                    error = ops.fused_adversarial_step(
-                        model.spec, model.entity_embedding, model.relation_embedding, sample, negative_sample,
-                        weight, mode, loss.alpha, modulus=model.kernel_modulus)
-                else:
+                    try:
+                        error = ops.fused_adversarial_step(
+                            model.spec, model.entity_embedding, model.relation_embedding, sample, negative_sample,
+                            weight, mode, loss.alpha, modulus=model.kernel_modulus)
+                    except ops.N.KgeError as e:
+                        if e.code != ops.N.E_UNSUPPORTED:
+                            raise
+                        fuse = False  # K too large for the fused kernel's shared memory: three-call route
+                if not fuse:
                     score = model(sample)
                     negative_score = model(sample=sample, negative_sample=negative_sample, mode=mode)
                     error = loss(score, negative_score, weight)

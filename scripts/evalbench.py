@@ -38,3 +38,18 @@ for name in args.model.split(","):
     t0 = time.time()
     out = ev.eval(m, [tuple(map(int, r)) for r in test[:512]])
     print(f"   Evaluation.eval on 512 triples (1024 rankings): {time.time()-t0:.2f} s wall -> {out}", flush=True)
+
+# K8: exact top-k of score rows against torch.topk / a full argsort (what utils.TopK replaced)
+for rows, cols, k in ((1, N, 10), (64, N, 100), (1024, N, 64)):
+    x = torch.randn(rows, cols, device=dev)
+    for name, fn in (("kge_topk_rows", lambda: ops.topk_rows(x, k)), ("torch.topk", lambda: torch.topk(x, k, dim=1)),
+                     ("torch.argsort[:k]", lambda: torch.argsort(x, dim=1, descending=True)[:, :k])):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        print(f"top-{k} of {rows} x {cols}: {name} {a.elapsed_time(b) / 10 * 1e3:.0f} us", flush=True)

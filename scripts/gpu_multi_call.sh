@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# Multi-GPU call (N = 2, 4 or 8): row-sharded table against the replicated column-parallel scheme.
+#   gpurun --gpus 2 --timeout 1200 -- 'bash scripts/gpu_multi_call.sh 2'
+set -u
+N=${1:-2}
+mkdir -p gpurun_out
+OUT=gpurun_out
+export PYTHONUNBUFFERED=1
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_sharded.py -m gpu -q -x 2>&1 | tail -30 > $OUT/pytest_multi_${N}gpu.log
+for cfg in cfg2 cfg4; do
+  for mode in colpar rowshard allreduce; do
+    timeout 300 $RUN bench.py --gpus $N --config $cfg --steps 100 --warmup 10 --mode $mode \
+        > $OUT/bench_${cfg}_${N}gpu_${mode}.json 2> $OUT/bench_${cfg}_${N}gpu_${mode}.err
+  done
+done
+NCCL_DEBUG=INFO timeout 200 $RUN bench.py --gpus $N --config cfg4 --steps 5 --warmup 3 --mode rowshard \
+    > $OUT/nccl_info_${N}gpu.log 2>&1
+ls -la $OUT

@@ -221,3 +221,29 @@ def test_protate_device_trainer_and_ranks():
                                      modulus=m0.modulus.item())
         got = ev.ranks(m0, q, mode).cpu().numpy()
         assert np.all(np.abs(got - ref) <= contested), (got, ref)
+
+
+def test_pipeline_falls_back_to_three_calls_when_k_exceeds_the_fused_kernel(capsys):
+    """K beyond one CTA's shared memory: the fused kernel reports KGE_E_UNSUPPORTED and Pipeline.learn
+    continues on the three-call route (model(sample); model(sample, neg, mode); loss)."""
+    from mkb_b200 import compose, datasets, optim, sampling
+
+    Nn, R, D, K = 120, 3, 8, 52000
+    rng = np.random.RandomState(0)
+    tri = [tuple(map(int, r)) for r in np.unique(np.stack([rng.randint(Nn, size=4), rng.randint(R, size=4),
+                                                          rng.randint(Nn, size=4)], 1), axis=0)]
+    ents, rels = {i: i for i in range(Nn)}, {i: i for i in range(R)}
+    torch.manual_seed(0)
+    m = models.TransE(hidden_dim=D, entities=ents, relations=rels, gamma=6.0).to(DEV)
+    before = m.entity_embedding.detach().clone()
+    ds = datasets.Dataset(train=tri, entities=ents, relations=rels, batch_size=4, seed=1)
+    ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=1)
+    with pytest.raises(ops.N.KgeError) as err:
+        s = torch.tensor(tri[:2]).to(DEV)
+        ops.fused_adversarial_step(m.spec, m.entity_embedding, m.relation_embedding, s, ns.generate(s, "tail-batch"),
+                                   torch.ones(2, device=DEV), "tail-batch")
+    assert err.value.code == ops.N.E_UNSUPPORTED
+    pipe = compose.Pipeline(epochs=1, device=DEV)
+    pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=optim.DenseAdam(m.parameters(), lr=1e-3),
+               loss=losses.Adversarial(0.5))
+    assert np.isfinite(pipe.metric_loss.get()) and not torch.equal(before, m.entity_embedding.detach())
