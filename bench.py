@@ -235,8 +235,8 @@ def run_ours(args):
     model = getattr(models, mname)(hidden_dim=D, entities={i: i for i in range(N)},
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
-                                   seed=42 + rank, device=dev)
-    topts = {"mode": args.mode, "backward": args.backward}
+                                   seed=42 + rank, device=dev, pool=args.pool)
+    topts = {"mode": args.mode, "backward": args.backward, "pooled_gemm": args.pooled_gemm}
     if args.virtual_shards:
         topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
     trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
@@ -357,6 +357,9 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_name(cfg), "global_batch": B * world, "negatives": K,
+                "sampler": ("independent on-device Philox draws" if args.pool == "independent" else
+                            "reference shared pool of 2K candidates per batch" +
+                            (", scored as one tensor-core GEMM" if trainer.pooled_gemm else "")),
                 "parallelism": (
                     "single GPU" if trainer.mode != "rowshard" else
                     f"single GPU, entity table in {trainer.n_shards} block-cyclic row shards (all local)")
@@ -426,6 +429,12 @@ def main():
     ap.add_argument("--backward", default="scatter", choices=["scatter", "by_entity"],
                     help="single-GPU backward: scatter = K3 vector REDs + dense Adam (default, the measured path); "
                          "by_entity = atomics-free per-entity backward with Adam fused in (csrc/byent.cu)")
+    ap.add_argument("--pool", default="independent", choices=["independent", "reference"],
+                    help="negative sampler: independent on-device draws (default, the headline) or the reference's "
+                         "shared pool of 2K candidates per batch")
+    ap.add_argument("--pooled-gemm", action="store_true",
+                    help="with --pool reference and DistMult/ComplEx (cfg3): score the batch as S = Q.Pool^T on the "
+                         "tensor cores (csrc/pooled.cu) instead of B*K row gathers")
     ap.add_argument("--virtual-shards", type=int, default=0,
                     help="single GPU only: run the row-sharded kernels with this many local shards")
     args = ap.parse_args()

@@ -243,6 +243,38 @@ int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, const int64_t
 int kge_filter_pool(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
                     int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,
                     int64_t* negatives, int32_t* status, kge_stream_t stream);
+/* Same, additionally returning positions[B,K] (int32, may be NULL): the index INTO THE POOL of every
+ * chosen negative — what the pooled tensor-core path (kge_pooled_dot_*) gathers its scores with. */
+int kge_filter_pool_positions(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
+                              int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,
+                              int64_t* negatives, int32_t* positions, int32_t* status, kge_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooled negatives on the tensor cores (csrc/pooled.cu) — DistMult / ComplEx training when the whole
+ *     batch shares ONE candidate pool, i.e. the reference's own sampler
+ *     (mkb/sampling/negative_sampling.py:166: one randint(n_entity, 2*size) pool per generate()).
+ *     All (1+K)·B scores are then entries of S[B,P] = Q·Pool^T (Q = per-positive query vectors h∘r /
+ *     conj(r)∘t, Pool = the P gathered rows), so K2 / K3's B·K row gathers become three small GEMMs on the
+ *     tcgen05 3xTF32 kernel (fp32 tiles when the shape does not allow): S = Q·Pool^T, dQ = dS·Pool,
+ *     dPool = dS^T·Q.  Replaces the same reference code as K2 / K3 (mkb/compose/pipeline.py:211-236,
+ *     distmult.py:63-75, complex.py:65-85, losses/adversarial.py:21-30) for that sampler.
+ * pool[P]: the batch's candidate ids; positions[B,K] (int32): index into the pool of each positive's K
+ *     negatives, from kge_filter_pool_positions.  Outputs as K2 (pos_score / neg_score optional).
+ * The backward ADDS into grad_entity / grad_relation like K3.  workspace: kge_pooled_workspace_bytes()
+ *     bytes, 16-byte aligned, uninitialised; it carries Q, Pool and dS from the forward to the backward,
+ *     so the same buffer must be passed to both, untouched in between.  loss_workspace: as K2's.
+ * KGE_E_UNSUPPORTED for the distance models (TransE / RotatE / pRotatE: their scores are not dot
+ *     products) — use K2 / K3.
+ * ------------------------------------------------------------------------------------------- */
+size_t kge_pooled_workspace_bytes(const kge_tables_t* tables, int64_t B, int64_t K, int64_t P);
+int kge_pooled_dot_fwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                       const int64_t* pool, int64_t P, const int32_t* positions, int64_t K,
+                       const float* weight, float alpha, float* pos_score, float* neg_score, float* coef_pos,
+                       float* stats, void* workspace, void* loss_workspace, kge_stream_t stream);
+int kge_pooled_dot_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
+                       const int64_t* pool, int64_t P, int64_t K, const float* coef_pos, const float* stats,
+                       const float* grad_loss, float* grad_entity, float* grad_relation, void* workspace,
+                       kge_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  filtered all-entity ranking.  Replaces TestDataset.__getitem__ (mkb/datasets/base.py:196-241)

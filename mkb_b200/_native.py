@@ -98,6 +98,13 @@ PROTOTYPES = {
                                        C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P]),
     "kge_filter_pool": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,
                                   _P, _P, _P]),
+    "kge_filter_pool_positions": (C.c_int, [C.POINTER(KgeFilterCsr), C.c_int, _P, _I64, _I64, _I64, _P, _I64,
+                                            _P, _P, _P, _P]),
+    "kge_pooled_workspace_bytes": (C.c_size_t, [C.POINTER(KgeTables), _I64, _I64, _I64]),
+    "kge_pooled_dot_fwd": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _P, _I64, _P, C.c_float,
+                                     _P, _P, _P, _P, _P, _P, _P]),
+    "kge_pooled_dot_bwd": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, _P, _I64, _I64, _P, _P, _P, _P, _P,
+                                     _P, _P]),
     "kge_rank_workspace_bytes": (C.c_size_t, [C.POINTER(KgeTables), _I64]),
     "kge_rank_all": (C.c_int, [C.POINTER(KgeTables), C.c_int, _P, _I64, C.POINTER(KgeFilterCsr), _P,
                                _P, _P, _P]),

@@ -92,7 +92,7 @@ class DeviceTrainer:
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,
-                 scalar_red=False, backward="scatter"):
+                 scalar_red=False, backward="scatter", pooled_gemm=False):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -129,6 +129,7 @@ class DeviceTrainer:
                 self.mode_note = f"colpar unavailable ({type(e).__name__}: {e}); using allreduce"
                 mode = "allreduce"
         self.mode = mode
+        self.pooled_gemm = False
         self.packed_records = bool(packed_records) and mode == "colpar"
         self.ent, self.rel = model.entity_embedding.data, model.relation_embedding.data
         # pRotatE: the trainable scalar modulus joins the step (single-GPU flow only)
@@ -173,6 +174,13 @@ class DeviceTrainer:
             self.coef_neg = torch.empty((max_batch, K), **f32)
             if self.backward == "by_entity":
                 self._byent_ws = ops.byent_workspace(self.spec, self.ent, self.rel, max_batch, K, self.modulus)
+            # opt-in: DistMult / ComplEx with the reference's shared pool score the whole batch as ONE GEMM
+            # S = Q·Pool^T on the tensor cores (csrc/pooled.cu) instead of B·K row gathers
+            self.pooled_gemm = (bool(pooled_gemm) and mode == "single" and sampling.pool == "reference"
+                                and self.spec.model_name in ("DistMult", "ComplEx"))
+            if self.pooled_gemm:
+                self.neg_pos = torch.empty((max_batch, K), dtype=torch.int32, device=self.dev)
+                self._pool_ws = ops.pooled_workspace(self.spec, self.ent, self.rel, max_batch, K, 2 * K)
 
     # ------------------------------------------------------------------------------------------
     # colpar set-up
@@ -352,7 +360,9 @@ class DeviceTrainer:
         if s.pool == "reference":  # the reference's host-drawn shared pool: 2K ids cross PCIe
             pool = torch.from_numpy(s._rng.randint(s.n_entity, size=self.K * 2).astype("int64")).to(
                 self.dev, non_blocking=True)
-            ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg)
+            self._pool = pool
+            ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg,
+                            positions=self.neg_pos[: sample.shape[0]] if self.pooled_gemm else None)
         else:
             ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status,
                                  neg, sort_rows=s.sort_rows)
@@ -374,6 +384,8 @@ class DeviceTrainer:
             h[0].record()
         packed = self.packed_records
         mod = self.modulus
+        if self.pooled_gemm:
+            return self._step_pooled(sample, weight, B, mode, h)
         ops.fused_forward_raw(self.spec, self.ent, self.rel, sample, neg, weight, mode, self.alpha, coef_pos,
                               coef_neg, self._stats_local if packed else self.stats, self.ws,
                               self.pos_score[:B] if mod is not None else None,
@@ -408,6 +420,24 @@ class DeviceTrainer:
                           zero_grad=True)
             ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps,
                           zero_grad=True)
+        return self.stats
+
+    def _step_pooled(self, sample, weight, B, mode, h):
+        """DistMult / ComplEx, reference pool: three GEMMs instead of B*K row gathers (csrc/pooled.cu)."""
+        coef_pos = self.coef_pos[:B]
+        ops.pooled_dot_forward_raw(self.spec, self.ent, self.rel, sample, self._pool, self.neg_pos[:B], weight, mode,
+                                   self.alpha, coef_pos, self.stats, self._pool_ws, self.ws)
+        if h:
+            h[1].record()
+            h[2].record()
+        self.t += 1
+        b1, b2 = self.betas
+        ops.pooled_dot_backward_raw(self.spec, self.ent, self.rel, sample, self._pool, self.K, mode, coef_pos,
+                                    self.stats, self.g_ent, self.g_rel, self._pool_ws)
+        if h:
+            h[3].record()
+        ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
         return self.stats
 
     def _step_colpar(self, sample, B, mode, h):

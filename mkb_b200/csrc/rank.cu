@@ -308,6 +308,52 @@ static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_ind
   return KGE_OK;
 }
 
+// out[M, N] = a[M, Kd] · b[N, Kd]^T in fp32-grade arithmetic: the ranking GEMM used as a plain "NT" GEMM
+// (pooled.cu).  It IS the DistMult score matrix of "queries" a against "entities" b, so it runs on the
+// tcgen05 3xTF32 kernel when the shape allows and on the fp32 tile kernel otherwise; the rank-counting
+// epilogue works on zeroed dummies.  scratch: dot_nt_scratch_bytes(M) bytes.
+namespace kge {
+size_t dot_nt_scratch_bytes(int64_t M) { return (size_t)M * (3 * 8 + 2 * 8 + 8 + 4) + 64; }
+
+int dot_nt_launch(const float* a, const float* b, int64_t M, int64_t N, int Kd, float* out, void* scratch,
+                  cudaStream_t st) {
+  if (M <= 0 || N <= 0 || Kd <= 0 || M > INT32_MAX / kTQ || N > INT32_MAX) return KGE_E_SIZE;
+  // "positive" id -1 for every row: no column is ever treated as the positive (the tcgen05 epilogue would
+  // substitute the prepared positive score there); everything else the rank epilogue reads is zero
+  cudaError_t ce = cudaMemsetAsync(scratch, 0xFF, (size_t)M * 3 * 8, st);
+  if (ce == cudaSuccess)
+    ce = cudaMemsetAsync(reinterpret_cast<char*>(scratch) + (size_t)M * 3 * 8, 0,
+                         dot_nt_scratch_bytes(M) - (size_t)M * 3 * 8, st);
+  if (ce != cudaSuccess) return (int)ce;
+  RankParams p{};
+  char* ws = reinterpret_cast<char*>(scratch);
+  p.queries = reinterpret_cast<const int64_t*>(ws);
+  ws += (size_t)M * 3 * 8;
+  p.seg = reinterpret_cast<int64_t*>(ws);
+  ws += (size_t)M * 2 * 8;
+  p.ranks = reinterpret_cast<unsigned long long*>(ws);
+  ws += (size_t)M * 8;
+  p.pos_score = reinterpret_cast<float*>(ws);
+  p.qmat = const_cast<float*>(a);
+  p.ent = b;
+  p.N = N;
+  p.n_global = N;
+  p.id_mul = 1;
+  p.Q = (int)M;
+  p.D = Kd;
+  p.ent_stride = Kd;
+  p.scores_out = out;
+  if (rank_tc_launch(a, b, N, Kd, p.queries, p.Q, nullptr, false, p.pos_score, p.seg, p.ranks, out, false, st) ==
+      KGE_OK)
+    return KGE_OK;
+  dim3 grid((unsigned)((M + kTQ - 1) / kTQ), (unsigned)((N + kTE - 1) / kTE));
+  if (grid.y > 65535) return KGE_E_SIZE;
+  rank_tile_kernel<KGE_DISTMULT, false><<<grid, kThreads, 0, st>>>(p);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}
+}  // namespace kge
+
 extern "C" int kge_rank_all(const kge_tables_t* t, int mode, const int64_t* queries, int64_t Q,
                             const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out,
                             void* workspace, kge_stream_t stream) {

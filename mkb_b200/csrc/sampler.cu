@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kThreads) filter_pool_kernel(kge_filter_csr_t 
                                                                int64_t B, int64_t K, int64_t n_entity,
                                                                const int64_t* __restrict__ pool,
                                                                int64_t pool_size,
-                                                               int64_t* __restrict__ out, int32_t* status) {
+                                                               int64_t* __restrict__ out, int32_t* status,
+                                                               int32_t* __restrict__ positions) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (i >= B) return;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kThreads) filter_pool_kernel(kge_filter_csr_t 
   lo = __shfl_sync(kFull, lo, 0);
   hi = __shfl_sync(kFull, hi, 0);
   int64_t* dst = out + i * K;
+  int32_t* pdst = positions ? positions + i * K : nullptr;  // index into the pool of every chosen negative
   int64_t cnt = 0;
   for (int64_t base = 0; base < pool_size && cnt < K; base += 32) {
     const int64_t k = base + lane;
@@ -160,17 +162,26 @@ __global__ void __launch_bounds__(kThreads) filter_pool_kernel(kge_filter_csr_t 
     const bool keep = k < pool_size && !is_member(f.members, lo, hi, x);
     const unsigned mask = __ballot_sync(kFull, keep);
     const int64_t pos = cnt + __popc(mask & ((1u << lane) - 1u));
-    if (keep && pos < K) dst[pos] = x;
+    if (keep && pos < K) {
+      dst[pos] = x;
+      if (pdst) pdst[pos] = (int32_t)k;
+    }
     cnt += __popc(mask);
   }
   __syncwarp();
   if (cnt == 0) {
     if (lane == 0) atomicOr(status, 4);
-    for (int64_t k = lane; k < K; k += 32) dst[k] = 0;
+    for (int64_t k = lane; k < K; k += 32) {
+      dst[k] = 0;
+      if (pdst) pdst[k] = 0;
+    }
     return;
   }
   // survivors repeat cyclically: dst[k] = dst[k mod cnt]  (np.concatenate of re-filtered pools)
-  for (int64_t k = cnt + lane; k < K; k += 32) dst[k] = dst[k % cnt];
+  for (int64_t k = cnt + lane; k < K; k += 32) {
+    dst[k] = dst[k % cnt];
+    if (pdst) pdst[k] = pdst[k % cnt];
+  }
 }
 
 }  // namespace kge
@@ -209,6 +220,14 @@ extern "C" int kge_sample_negatives(const kge_filter_csr_t* filter, int mode, co
 extern "C" int kge_filter_pool(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
                                int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,
                                int64_t* negatives, int32_t* status, kge_stream_t stream) {
+  return kge_filter_pool_positions(filter, mode, sample, B, K, n_entity, pool, pool_size, negatives, nullptr, status,
+                                   stream);
+}
+
+extern "C" int kge_filter_pool_positions(const kge_filter_csr_t* filter, int mode, const int64_t* sample, int64_t B,
+                                         int64_t K, int64_t n_entity, const int64_t* pool, int64_t pool_size,
+                                         int64_t* negatives, int32_t* positions, int32_t* status,
+                                         kge_stream_t stream) {
   int rc = check_filter(filter);
   if (rc) return rc;
   if (!sample || !negatives || !status || !pool) return KGE_E_NULL;
@@ -216,7 +235,7 @@ extern "C" int kge_filter_pool(const kge_filter_csr_t* filter, int mode, const i
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   if (B == 0) return KGE_OK;
   filter_pool_kernel<<<(unsigned)((B + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(
-      *filter, mode == KGE_HEAD_BATCH, sample, B, K, n_entity, pool, pool_size, negatives, status);
+      *filter, mode == KGE_HEAD_BATCH, sample, B, K, n_entity, pool, pool_size, negatives, status, positions);
   KGE_LAUNCH_CHECK();
   return KGE_OK;
 }

@@ -623,7 +623,9 @@ def sample_negatives(csr, sample, mode, size, n_entity, seed, offset, status=Non
     return out, status
 
 
-def filter_pool(csr, sample, mode, size, n_entity, pool, status=None, out=None):
+def filter_pool(csr, sample, mode, size, n_entity, pool, status=None, out=None, positions=None):
+    """Reference-pool negatives; ``positions`` (int32 ``[B,size]``, optional) additionally receives the index
+    into ``pool`` of every chosen negative (what the pooled tensor-core step gathers its scores with)."""
     lib = N.load()
     N.require_cuda(sample, csr.keys, pool)
     B = sample.shape[0]
@@ -634,11 +636,47 @@ def filter_pool(csr, sample, mode, size, n_entity, pool, status=None, out=None):
         status = torch.zeros(1, dtype=torch.int32, device=dev)
     fs = csr.struct()
     with torch.cuda.device(dev):
-        N.check(lib.kge_filter_pool(C.byref(fs), _mode_id(mode), N.ptr(sample), B, size, n_entity,
-                                    N.ptr(pool), pool.shape[0], N.ptr(out), N.ptr(status),
-                                    N.stream_ptr(dev)), "kge_filter_pool")
+        if positions is not None and (positions.dtype != torch.int32 or not positions.is_contiguous()):
+            raise TypeError("positions must be a contiguous int32 tensor")
+        N.check(lib.kge_filter_pool_positions(C.byref(fs), _mode_id(mode), N.ptr(sample), B, size, n_entity,
+                                              N.ptr(pool), pool.shape[0], N.ptr(out), N.ptr(positions), N.ptr(status),
+                                              N.stream_ptr(dev)), "kge_filter_pool_positions")
     N.count_launch()
     return out, status
+
+
+# ---------------------------------------------------------------------------------------------
+# pooled negatives on the tensor cores (DistMult / ComplEx with the reference's shared pool)
+# ---------------------------------------------------------------------------------------------
+def pooled_workspace(spec, ent, rel, B, K, P):
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    return torch.empty(max(lib.kge_pooled_workspace_bytes(C.byref(tb), B, K, P), 256), dtype=torch.uint8,
+                       device=ent.device)
+
+
+def pooled_dot_forward_raw(spec, ent, rel, sample, pool, positions, weight, mode, alpha, coef_pos, stats, workspace,
+                           loss_ws, pos_score=None, neg_score=None):
+    """S = Q·Pool^T + self-adversarial terms (kge_pooled_dot_fwd); keeps Q, Pool and dS in ``workspace``."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    B, K = positions.shape
+    N.check(lib.kge_pooled_dot_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), B, N.ptr(pool), pool.shape[0],
+                                   N.ptr(positions), K, N.ptr(weight), alpha, N.ptr(pos_score), N.ptr(neg_score),
+                                   N.ptr(coef_pos), N.ptr(stats), N.ptr(workspace), N.ptr(loss_ws),
+                                   N.stream_ptr(ent.device)), "kge_pooled_dot_fwd")
+    N.count_launch(5)
+
+
+def pooled_dot_backward_raw(spec, ent, rel, sample, pool, K, mode, coef_pos, stats, g_ent, g_rel, workspace,
+                            grad_loss=None):
+    """dQ = dS·Pool, dPool = dS^T·Q, chain rule and row scatter (kge_pooled_dot_bwd): ADDS into g_ent / g_rel."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    N.check(lib.kge_pooled_dot_bwd(C.byref(tb), _mode_id(mode), N.ptr(sample), sample.shape[0], N.ptr(pool),
+                                   pool.shape[0], K, N.ptr(coef_pos), N.ptr(stats), N.ptr(grad_loss), N.ptr(g_ent),
+                                   N.ptr(g_rel), N.ptr(workspace), N.stream_ptr(ent.device)), "kge_pooled_dot_bwd")
+    N.count_launch(8)
 
 
 # ---------------------------------------------------------------------------------------------

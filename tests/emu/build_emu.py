@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mkb_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libkge_emu.so")
-SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu", "byent.cu"]
+SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu", "byent.cu", "pooled.cu"]
 HEADERS = ["kge_common.cuh"]
 
 

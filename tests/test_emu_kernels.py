@@ -523,3 +523,63 @@ def test_by_entity_backward_huge_buckets():
                                   0.9, 0.999, 1e-8, wsp, None))
     np.testing.assert_allclose(m1, m_ref, rtol=1e-4, atol=1e-6 * np.abs(ge).max())
     assert np.abs((p1 - ent) - (p_ref - ent)).max() <= 2e-3 * np.abs(p_ref - ent).max()
+
+
+@pytest.mark.parametrize("model", ("DistMult", "ComplEx"))
+@pytest.mark.parametrize("mode", MODES)
+def test_pooled_dot_step_equals_fused_step_on_the_same_negatives(model, mode, sampler_cases):
+    """kge_pooled_dot_fwd/bwd (S = Q·Pool^T and two backward GEMMs; fp32 tiles here, tcgen05 on the GPU)
+    == kge_fused_fwd/bwd fed the negatives kge_filter_pool selects from the same pool."""
+    l = H.lib()
+    g = sampler_cases
+    triples = [tuple(int(x) for x in r) for r in g["triples"]]
+    Nn, R, D, K, gamma = int(g["N"]), int(g["R"]), 12, 16, 9.0
+    ent, rel = ko.init_tables(model, Nn, R, D, gamma, seed=3)
+    ent *= 3.0
+    sample = np.ascontiguousarray(g["gen0/sample"], np.int64)
+    B = sample.shape[0]
+    rng = np.random.RandomState(8)
+    w = rng.uniform(0.1, 0.5, B).astype(np.float32)
+    pool = rng.randint(Nn, size=2 * K).astype(np.int64)
+    pool[5] = pool[2]  # a repeated id inside the pool
+    P = pool.shape[0]
+    csr = ko.build_filter_csr(triples, Nn, "head" if mode == "head-batch" else "tail")
+    fs = H.csr_struct(csr)
+    neg, pos_idx = np.full((B, K), -1, np.int64), np.full((B, K), -1, np.int32)
+    status = np.zeros(1, np.int32)
+    H.ok(l.kge_filter_pool_positions(C.byref(fs), H.mode_id(mode), H.P(sample), B, K, Nn, H.P(pool), P, H.P(neg),
+                                     H.P(pos_idx), H.P(status), None))
+    assert status[0] == 0 and np.array_equal(pool[pos_idx], neg)
+    neg2 = np.full((B, K), -1, np.int64)
+    H.ok(l.kge_filter_pool(C.byref(fs), H.mode_id(mode), H.P(sample), B, K, Nn, H.P(pool), P, H.P(neg2), H.P(status), None))
+    assert np.array_equal(neg, neg2)
+    # reference: the fused kernels on those negatives
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    ge, gr = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f)
+    # pooled path
+    tb = H.tables(model, ent, rel, gamma)
+    ws = np.full(l.kge_pooled_workspace_bytes(C.byref(tb), B, K, P) + 64, 0xCD, np.uint8)
+    wsp = (ws.ctypes.data + 63) & ~63
+    lws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, np.uint8)
+    ps, ns = np.full((B, 1), np.nan, np.float32), np.full((B, K), np.nan, np.float32)
+    cpos, stats = np.full(B, np.nan, np.float32), np.zeros(4, np.float32)
+    H.ok(l.kge_pooled_dot_fwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(pool), P, H.P(pos_idx), K, H.P(w), 0.5,
+                              H.P(ps), H.P(ns), H.P(cpos), H.P(stats), wsp, H.P(lws), None), "kge_pooled_dot_fwd")
+    _close(ps, f["pos"].astype(np.float64), 1e-5)
+    _close(ns, f["neg"].astype(np.float64), 1e-5)
+    np.testing.assert_allclose(cpos, f["cpos"], rtol=1e-5)
+    np.testing.assert_allclose(stats, f["stats"], rtol=1e-5)
+    g_ent, g_rel = np.zeros_like(ent), np.zeros_like(rel)
+    H.ok(l.kge_pooled_dot_bwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(pool), P, K, H.P(cpos), H.P(stats), None,
+                              H.P(g_ent), H.P(g_rel), wsp, None), "kge_pooled_dot_bwd")
+    _grad_close(g_ent, ge.astype(np.float64), 1e-5)
+    _grad_close(g_rel, gr.astype(np.float64), 1e-5)
+    # and against the oracle
+    loss, _, _, ge64, gr64 = ko.train_step(model, ent, rel, sample, neg, mode, w, gamma=gamma)
+    assert abs(stats[3] - loss) <= 1e-5 * abs(loss)
+    _grad_close(g_ent, ge64)
+    _grad_close(g_rel, gr64)
+    # distance models are refused
+    tb2 = H.tables("RotatE", *ko.init_tables("RotatE", Nn, R, D, gamma, seed=1), gamma)
+    assert l.kge_pooled_dot_fwd(C.byref(tb2), 0, H.P(sample), B, H.P(pool), P, H.P(pos_idx), K, H.P(w), 0.5, None, None,
+                                H.P(cpos), H.P(stats), wsp, H.P(lws), None) == -6

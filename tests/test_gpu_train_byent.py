@@ -83,3 +83,42 @@ def test_by_entity_full_size_step_matches_scatter():
     assert u0.abs().max().item() > 0
     assert ((u0 - u1).abs() > 0.05 * u0.abs().max()).float().mean().item() < 1e-3
     assert ((r0 - r1).abs() > 3e-4).float().mean().item() < 1e-2
+
+
+@pytest.mark.parametrize("model", ("ComplEx", "DistMult"))
+def test_pooled_gemm_trainer_tracks_gather_trainer(model):
+    """pool='reference' + pooled_gemm=True (S = Q·Pool^T on the tensor cores, csrc/pooled.cu) follows the
+    gather kernels on the same pools: same losses, same updates up to summation order / 3xTF32 rounding."""
+    Nn, R, D, B, K, gamma = 800, 7, 64, 48, 32, 9.0
+    rng = np.random.RandomState(0)
+    tri = np.unique(np.stack([rng.randint(Nn, size=8000), rng.randint(R, size=8000), rng.randint(Nn, size=8000)], 1), axis=0)
+    w_all = torch.from_numpy(rng.uniform(0.1, 0.5, len(tri)).astype(np.float32)).to(DEV)
+    T = torch.from_numpy(tri).to(DEV)
+    out = []
+    for pooled in (False, True):
+        torch.manual_seed(3)
+        m = getattr(models, model)(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                                   gamma=gamma).to(DEV)
+        with torch.no_grad():
+            m.entity_embedding.mul_(3.0)
+        init = m.entity_embedding.detach().clone()
+        ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=range(Nn), relations=range(R), seed=7,
+                                       pool="reference")
+        tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, pooled_gemm=pooled)
+        assert tr.pooled_gemm == pooled
+        losses = []
+        for step in range(5):
+            idx = torch.arange(step * B, (step + 1) * B, device=DEV)
+            tr.step(T[idx], w_all[idx], "head-batch" if step % 2 == 0 else "tail-batch")
+            losses.append(tr.loss())
+        ns.check_status(DEV)
+        out.append((m.entity_embedding.detach() - init, m.relation_embedding.detach().clone(), losses))
+    (u0, r0, l0), (u1, r1, l1) = out
+    assert np.allclose(l0, l1, rtol=1e-4), (l0, l1)
+    assert u0.abs().max().item() > 0
+    assert ((u0 - u1).abs() > 0.05 * u0.abs().max()).float().mean().item() < 1e-3
+    assert ((r0 - r1).abs() > 3e-4).float().mean().item() < 1e-2
+    # a distance model silently keeps the gather kernels
+    m = models.RotatE(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                      gamma=gamma).to(DEV)
+    assert not DeviceTrainer(m, ns, max_batch=B, pooled_gemm=True).pooled_gemm
