@@ -19,6 +19,11 @@ for cfg in cfg2 cfg1 cfg3 cfg4; do
   timeout 300 python bench.py --config $cfg --steps 200 --warmup 10 --no-cpu-baseline --backward by_entity \
       > $OUT/bench_${cfg}_byent.json 2> $OUT/bench_${cfg}_byent.err
 done
+# config 3 with the reference's shared pool: gather kernels vs the tensor-core GEMM formulation
+timeout 300 python bench.py --config cfg3 --steps 200 --warmup 10 --no-cpu-baseline --pool reference \
+    > $OUT/bench_cfg3_pool_gather.json 2> $OUT/bench_cfg3_pool_gather.err
+timeout 300 python bench.py --config cfg3 --steps 200 --warmup 10 --no-cpu-baseline --pool reference --pooled-gemm \
+    > $OUT/bench_cfg3_pool_gemm.json 2> $OUT/bench_cfg3_pool_gemm.err
 # row-sharded kernels with all shards local (addressing overhead only; NVLink needs scripts/gpu_multi_call.sh)
 timeout 300 python bench.py --config cfg4 --steps 100 --warmup 10 --no-cpu-baseline --virtual-shards 4 \
     > $OUT/bench_cfg4_vshard4.json 2> $OUT/bench_cfg4_vshard4.err
