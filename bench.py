@@ -375,7 +375,9 @@ def run_ours(args):
                         f" [{trainer.mode_note}]" if trainer.mode_note else "")),
                 "l2": "working set per step (tables+grads+Adam moments = "
                       f"{4 * (N * row_e + R * row_r) / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
-                "step": ("sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
+                "step": ("filter_pool + pooled_dot_fwd (gather P rows, GEMM S=Q.Pool^T, adv terms) + pooled_dot_bwd "
+                         "(2 GEMMs, chain, row scatter) + adam(entity) + adam(relation)" if trainer.pooled_gemm else
+                         "sample_negatives + fused_fwd + fused_bwd + adam(entity) + adam(relation)"
                          if trainer.backward == "scatter" else
                          "sample_negatives + fused_fwd + by-entity backward (CSR build, queries, dq pass, per-entity "
                          "gradient + Adam in place) + adam(relation)")
