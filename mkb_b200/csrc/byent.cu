@@ -146,7 +146,7 @@ template <int M>
 __global__ void __launch_bounds__(kThreads, 4) byent_apply_kernel(ByEntParams p) {
   using T = Traits<M>;
   __shared__ unsigned int s_ent[kMaxBucket];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;  // 32..256 threads: one 16-byte chunk of the row each
   const int64_t e = blockIdx.x;
   const unsigned lo = p.offsets[e], hi = p.offsets[e + 1];
   const int n = (int)(hi - lo);
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(kThreads, 4) byent_apply_kernel(ByEntParams p)
     // the scatter's order depends on atomics: sort the bucket so the sums below have ONE order
     int p2 = 1;
     while (p2 < n) p2 <<= 1;
-    for (int k = tid; k < p2; k += kThreads) s_ent[k] = k < n ? p.entries[lo + k] : 0xFFFFFFFFu;
+    for (int k = tid; k < p2; k += nthr) s_ent[k] = k < n ? p.entries[lo + k] : 0xFFFFFFFFu;
     __syncthreads();
     for (int size = 2; size <= p2; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = tid; t < (p2 >> 1); t += kThreads) {
+        for (int t = tid; t < (p2 >> 1); t += nthr) {
           const int a_i = 2 * t - (t & (stride - 1)), b_i = a_i + stride;
           const bool up = (a_i & size) == 0;
           const unsigned a = s_ent[a_i], b = s_ent[b_i];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 4) byent_apply_kernel(ByEntParams p)
   float* row = p.ent + e * (int64_t)p.ent_stride;
   float* mrow = p.exp_avg + e * (int64_t)p.ent_stride;
   float* vrow = p.exp_avg_sq + e * (int64_t)p.ent_stride;
-  for (int d = tid * 4; d < p.D; d += kThreads * 4) {
+  for (int d = tid * 4; d < p.D; d += nthr * 4) {
     float e0[4], e1[4] = {}, g0[4] = {}, g1[4] = {};
     ld_global<4>(row + d, e0);
     if constexpr (T::NC == 2) ld_global<4>(row + p.D + d, e1);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) byrel_apply_kernel(ByEntParams p) {
   float* row = p.rel_w + r * (int64_t)p.rel_stride;
   float* mrow = p.rel_exp_avg + r * (int64_t)p.rel_stride;
   float* vrow = p.rel_exp_avg_sq + r * (int64_t)p.rel_stride;
-  for (int d = threadIdx.x * 4; d < p.rel_stride; d += kThreads * 4) {
+  for (int d = threadIdx.x * 4; d < p.rel_stride; d += blockDim.x * 4) {
     float g[4] = {};
     for (int i = 0; i < p.B; ++i) {
       if (__ldg(p.sample + 3 * (int64_t)i + 1) != r) continue;  // uniform over the CTA
@@ -391,8 +391,11 @@ extern "C" int kge_bwd_by_entity_adam(const kge_tables_t* t, int mode, const int
   KGE_LAUNCH_CHECK();
   int rc = dq_pass_launch(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, gh, gt, gr, st);
   if (rc) return rc;
+  // one thread per 16-byte chunk of a row component, 32..256 threads per entity
+  int apply_threads = ((p.D / 4 + 31) / 32) * 32;
+  apply_threads = apply_threads < 32 ? 32 : (apply_threads > kThreads ? kThreads : apply_threads);
 #define KGE_CASE(MM) \
-  case MM: byent_apply_kernel<MM><<<(unsigned)p.N, kThreads, 0, st>>>(p); break;
+  case MM: byent_apply_kernel<MM><<<(unsigned)p.N, apply_threads, 0, st>>>(p); break;
   switch (t->model) {
     KGE_CASE(KGE_TRANSE)
     KGE_CASE(KGE_DISTMULT)
@@ -401,7 +404,9 @@ extern "C" int kge_bwd_by_entity_adam(const kge_tables_t* t, int mode, const int
     KGE_CASE(KGE_PROTATE)
   }
 #undef KGE_CASE
-  byrel_apply_kernel<<<(unsigned)t->n_relation, kThreads, 0, st>>>(p);
+  int rel_threads = ((p.rel_stride / 4 + 31) / 32) * 32;
+  rel_threads = rel_threads < 32 ? 32 : (rel_threads > kThreads ? kThreads : rel_threads);
+  byrel_apply_kernel<<<(unsigned)t->n_relation, rel_threads, 0, st>>>(p);
   KGE_LAUNCH_CHECK();
   return KGE_OK;
 }
