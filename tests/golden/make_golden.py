@@ -341,6 +341,14 @@ def gen_next_rows():
         out[f"{name}/top_relations"] = np.array([relations[r] for r in topk.top_relations(k=2, model=model, head=4, tail="e9")])
         out[f"{name}/prediction"] = _np(utils.make_prediction(model=model, dataset=test[:9], batch_size=4, num_workers=0,
                                                               device="cpu"))
+        # triplet classification (evaluation/classif.py): true test triples vs the same with a shifted tail
+        X = list(test) + [(h, r, (t + 7) % N) for h, r, t in test]
+        y = [1] * len(test) + [-1] * len(test)
+        out["clf/X"], out["clf/y"] = np.array(X, dtype=np.int64), np.array(y, dtype=np.int64)
+        thr = evaluation.find_threshold(model=model, X=X, y=y, batch_size=8, num_workers=0, device="cpu")
+        out[f"{name}/threshold"] = np.float64(thr)
+        out[f"{name}/accuracy"] = np.float64(evaluation.accuracy(model=model, X=X, y=y, threshold=thr, batch_size=8,
+                                                                 num_workers=0, device="cpu"))
     # pRotatE: forward / loss / autograd gradients (fp32 and fp64), both modes, vector and scalar dims
     for D in (8, 5):
         for mode in ("tail-batch", "head-batch"):

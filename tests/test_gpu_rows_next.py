@@ -247,3 +247,16 @@ def test_pipeline_falls_back_to_three_calls_when_k_exceeds_the_fused_kernel(caps
     pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=optim.DenseAdam(m.parameters(), lr=1e-3),
                loss=losses.Adversarial(0.5))
     assert np.isfinite(pipe.metric_loss.get()) and not torch.equal(before, m.entity_embedding.detach())
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_triplet_classification_matches_reference(g, model):
+    """evaluation.find_threshold / accuracy (mkb/evaluation/classif.py) on the positives kernel."""
+    m, _, _, _, _ = _setup(g, model)
+    X = [tuple(int(v) for v in r) for r in g["clf/X"]]
+    y = [int(v) for v in g["clf/y"]]
+    thr = evaluation.find_threshold(model=m, X=X, y=y, batch_size=8, device=DEV)
+    ref = float(g[f"{model}/threshold"])
+    assert abs(thr - ref) <= 1e-4 * max(abs(ref), 1.0)
+    acc = evaluation.accuracy(model=m, X=X, y=y, threshold=ref, batch_size=8, device=DEV)
+    assert abs(acc - float(g[f"{model}/accuracy"])) <= 1.0 / len(X) + 1e-9

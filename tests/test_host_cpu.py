@@ -298,3 +298,34 @@ def test_types_relations_and_detail_frame_match_reference(next_rows, name, monke
 
     frame2 = ev._detail_frame(pd, metrics, by_id)
     np.testing.assert_allclose(frame2.to_numpy(dtype=np.float64), g[f"{name}/detail"], atol=1e-4)
+
+
+def test_classification_threshold_matches_sklearn_and_reference(next_rows):
+    """evaluation.find_threshold / accuracy (mkb/evaluation/classif.py): the numpy threshold search equals
+    sklearn's roc_curve + argmax on random scores with ties, and the reference's outputs on the golden graph."""
+    from sklearn import metrics
+
+    from mkb_b200 import evaluation
+    from mkb_b200.evaluation.classif import _accuracy, best_threshold
+
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        n = rng.randint(2, 40)
+        y = np.where(rng.rand(n) < 0.5, 1, -1)
+        if abs(y.sum()) == n:
+            y[0] = -y[0]
+        score = np.round(rng.normal(size=n), 1 if trial % 2 else 3).astype(np.float32)
+        fpr, tpr, thr = metrics.roc_curve(y_true=y, y_score=score)
+        assert best_threshold(y, score) == thr[np.argmax(tpr - fpr)], (y, score)
+    assert best_threshold([-1, -1, -1, -1, -1, 1, 1, 1, 1, 1], [1, 2, 3, 4, 5, 5, 6, 7, 8, 9]) == 6  # classif.py:95-107
+    assert _accuracy(np.array([1, 2, 3, 4, 5, 5, 6, 7, 8, 9]), np.array([-1] * 5 + [1] * 5), 5) == 0.9  # :130-133
+    g = next_rows
+    X = [tuple(int(v) for v in r) for r in g["clf/X"]]
+    y = [int(v) for v in g["clf/y"]]
+    for name in ("TransE", "RotatE"):
+        m = _OracleModel(name, g[f"{name}/ent"].astype(np.float64), g[f"{name}/rel"].astype(np.float64),
+                         float(g[f"{name}/gamma"]))
+        thr = evaluation.find_threshold(model=m, X=X, y=y, batch_size=8, device="cpu")
+        assert abs(thr - float(g[f"{name}/threshold"])) <= 1e-4 * abs(thr)
+        acc = evaluation.accuracy(model=m, X=X, y=y, threshold=float(g[f"{name}/threshold"]), batch_size=8, device="cpu")
+        assert abs(acc - float(g[f"{name}/accuracy"])) <= 1.0 / len(X) + 1e-9
