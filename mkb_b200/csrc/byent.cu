@@ -151,8 +151,24 @@ __global__ void __launch_bounds__(kThreads, 4) byent_apply_kernel(ByEntParams p)
   const unsigned lo = p.offsets[e], hi = p.offsets[e + 1];
   const int n = (int)(hi - lo);
   const bool sorted = n <= kMaxBucket;
-  if (sorted && n > 0) {
-    // the scatter's order depends on atomics: sort the bucket so the sums below have ONE order
+  if (n > 0 && n <= 32) {
+    // the scatter's order depends on atomics: sort the bucket so the sums below have ONE order.
+    // The common case (a few dozen entries) is a shuffle-only bitonic network in warp 0: one barrier.
+    if (tid < 32) {
+      unsigned v = tid < n ? __ldg(p.entries + lo + tid) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          const unsigned other = __shfl_xor_sync(kFull, v, stride);
+          const bool up = (tid & size) == 0, lower = (tid & stride) == 0;
+          v = (lower == up) ? min(v, other) : max(v, other);
+        }
+      }
+      s_ent[tid] = v;
+    }
+    __syncthreads();
+  } else if (sorted && n > 0) {
     int p2 = 1;
     while (p2 < n) p2 <<= 1;
     for (int k = tid; k < p2; k += nthr) s_ent[k] = k < n ? p.entries[lo + k] : 0xFFFFFFFFu;

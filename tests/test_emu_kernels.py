@@ -504,10 +504,12 @@ def test_by_entity_backward_with_fused_adam_equals_scatter_plus_adam(model, mode
                                     1e-3, 0.9, 0.999, 1e-8, wsp, None) == -6
 
 
-def test_by_entity_backward_huge_buckets():
-    """Buckets larger than the in-kernel sort capacity (2048 entries per entity) take the unsorted path."""
+@pytest.mark.parametrize("Nn,B,K", [(3, 30, 250), (5, 10, 40)])
+def test_by_entity_backward_huge_buckets(Nn, B, K):
+    """Buckets larger than the in-kernel sort capacity (2048 entries per entity) take the unsorted path;
+    buckets of 33..2048 entries the shared-memory bitonic sort (the warp-shuffle sort covers <= 32)."""
     l = H.lib()
-    model, mode, Nn, R, D, B, K, gamma = "TransE", "tail-batch", 3, 2, 4, 30, 250, 6.0
+    model, mode, R, D, gamma = "TransE", "tail-batch", 2, 4, 6.0
     ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=2)
     f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
     ge, gr = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f)
