@@ -181,6 +181,39 @@ def cpu_reference_run(cfg, steps, warmup, budget_s, graph=None):
     }
 
 
+def eager_gpu_run(cfg, graph, dev, steps=5, warmup=2):
+    """The reference's eager-PyTorch operator sequence (oracle/torch_port.py) on THIS GPU, full batch — what a
+    user gets from the reference with device='cuda' (SURVEY §8(d)).  Its sampler stays on the host as in the
+    reference (Python loop over the positives), so two numbers are reported: the whole step and the device
+    part alone.  Part of the baseline leg: never the thing shipped."""
+    from oracle import torch_port as tp
+
+    ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    tri = [tuple(r) for r in graph.tolist()]
+    th, tt = tp.true_sets(tri)
+    trainer = tp.CpuTrainer(model, N, R, D, gamma, lr=5e-5, seed=42, device=dev)
+    rng, pick = np.random.RandomState(42), np.random.RandomState(1)
+    t_all = t_dev = 0.0
+    for i in range(warmup + steps):
+        idx = pick.choice(len(tri), B, replace=False)
+        s, w = torch.tensor([tri[j] for j in idx]), torch.full((B,), 0.3)
+        mode = "head-batch" if i % 2 == 0 else "tail-batch"
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        neg = tp.generate_negatives(rng, s, mode, th, tt, N, K)
+        s_d, w_d, neg_d = s.to(dev), w.to(dev), neg.to(dev)
+        t1 = time.perf_counter()
+        trainer.step(s_d, w_d, mode, neg_d)  # ends with error.item(): synchronises
+        t2 = time.perf_counter()
+        if i >= warmup:
+            t_all += t2 - t0
+            t_dev += t2 - t1
+    return {"value": B * (1 + K) * steps / t_all, "device_part_only": B * (1 + K) * steps / t_dev, "unit": UNIT,
+            "steps": steps, "ms_per_step": 1e3 * t_all / steps, "device_ms_per_step": 1e3 * t_dev / steps,
+            "what": "oracle/torch_port.py (the reference's ATen sequence + torch.optim.Adam) on cuda:0, full batch; "
+                    "host-side reference sampler included in `value`, excluded in `device_part_only`"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -409,6 +442,12 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_reference_run(cfg, steps=3, warmup=1, budget_s=20.0, graph=graph)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:  # informative only: must never cost the bench line
+                del trainer, model2, opt, pipe
+                torch.cuda.empty_cache()
+                line["cpu_baseline"]["same_operators_on_this_gpu"] = eager_gpu_run(cfg, graph, dev)
+            except Exception as e:  # e.g. out of memory for the eager path's [B,K,2D] temporaries
+                line["cpu_baseline"]["same_operators_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line))
     if dist:
         torch.distributed.barrier()

@@ -122,7 +122,9 @@ class CpuTrainer:
     """The loop body of mkb/compose/pipeline.py:206-242 on CPU tensors with a dense torch Adam
     (README.md:123-126).  ``step`` returns the loss as a Python float (``error.item()``, :242)."""
 
-    def __init__(self, model, n_entity, n_relation, hidden_dim, gamma, lr=5e-5, seed=42, alpha=0.5):
+    def __init__(self, model, n_entity, n_relation, hidden_dim, gamma, lr=5e-5, seed=42, alpha=0.5, device="cpu"):
+        """``device="cuda"`` runs the SAME eager operator sequence on a GPU (what the reference does with
+        ``device='cuda'``): bench.py reports it next to the CPU baseline, SURVEY §8(d)."""
         from .kge_oracle import embedding_range, entity_dim, relation_dim
 
         self.model, self.gamma, self.alpha = model, float(gamma), alpha
@@ -130,8 +132,10 @@ class CpuTrainer:
         self.embedding_range = embedding_range(gamma, hidden_dim)
         g = torch.Generator().manual_seed(seed)
         r = self.embedding_range
-        self.ent = torch.nn.Parameter((torch.rand(n_entity, entity_dim(model, hidden_dim), generator=g) * 2 - 1) * r)
-        self.rel = torch.nn.Parameter((torch.rand(n_relation, relation_dim(model, hidden_dim), generator=g) * 2 - 1) * r)
+        self.ent = torch.nn.Parameter(
+            ((torch.rand(n_entity, entity_dim(model, hidden_dim), generator=g) * 2 - 1) * r).to(device))
+        self.rel = torch.nn.Parameter(
+            ((torch.rand(n_relation, relation_dim(model, hidden_dim), generator=g) * 2 - 1) * r).to(device))
         self.opt = torch.optim.Adam([self.ent, self.rel], lr=lr)
 
     def step(self, sample, weight, mode, negative_sample):
