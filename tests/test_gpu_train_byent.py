@@ -122,3 +122,54 @@ def test_pooled_gemm_trainer_tracks_gather_trainer(model):
     m = models.RotatE(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
                       gamma=gamma).to(DEV)
     assert not DeviceTrainer(m, ns, max_batch=B, pooled_gemm=True).pooled_gemm
+
+
+def test_pooled_gemm_full_size_step_matches_gather():
+    """Config-3 shapes (ComplEx D=1000, B=1024, K=256, pool of 512): the three-GEMM step == the gather step."""
+    Nn, R, D, B, K, gamma = 14541, 237, 1000, 1024, 256, 9.0
+    rng = np.random.RandomState(0)
+    tri = np.unique(np.stack([rng.randint(Nn, size=60000), rng.randint(R, size=60000), rng.randint(Nn, size=60000)], 1), axis=0)
+    s = torch.from_numpy(tri[:B]).to(DEV)
+    w = torch.from_numpy(rng.uniform(0.1, 0.5, B).astype(np.float32)).to(DEV)
+    out = []
+    for pooled in (False, True):
+        torch.manual_seed(1)
+        m = models.ComplEx(hidden_dim=D, entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)},
+                           gamma=gamma).to(DEV)
+        with torch.no_grad():
+            m.entity_embedding.mul_(20.0)  # scores of order 1 so the softmax weights are not uniform
+            m.relation_embedding.mul_(20.0)
+        init = m.entity_embedding.detach().clone()
+        ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=range(Nn), relations=range(R), seed=3,
+                                       pool="reference")
+        tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, pooled_gemm=pooled)
+        tr.step(s, w, "tail-batch")
+        l_first = tr.loss()
+        tr.step(s, w, "head-batch")
+        out.append((m.entity_embedding.detach() - init, l_first, tr.loss()))
+    (u0, a0, b0), (u1, a1, b1) = out
+    assert abs(a0 - a1) <= 1e-5 * abs(a0) and abs(b0 - b1) <= 1e-4 * abs(b0)
+    assert u0.abs().max().item() > 0
+    assert ((u0 - u1).abs() > 0.05 * u0.abs().max()).float().mean().item() < 1e-3
+
+
+def test_kl_divergence_full_size_properties():
+    """[1024, 14541] score matrices: KL >= 0, == 0 for identical inputs, invariant to per-row shifts, and both
+    gradients sum to zero along every row (softmax is shift-invariant)."""
+    from mkb_b200 import losses
+
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    s = (3 * torch.randn(1024, 14541, device=DEV, generator=gen)).requires_grad_()
+    t = (3 * torch.randn(1024, 14541, device=DEV, generator=gen)).requires_grad_()
+    kl = losses.KlDivergence()
+    loss = kl(s, t, T=2)
+    loss.backward()
+    assert loss.item() > 0
+    assert kl(s.detach(), s.detach(), T=2).item() == pytest.approx(0.0, abs=1e-9)
+    shift = torch.randn(1024, 1, device=DEV, generator=gen)
+    assert kl(s.detach() + shift, t.detach() - shift, T=2).item() == pytest.approx(loss.item(), rel=1e-4)
+    assert s.grad.sum(1).abs().max().item() <= 1e-3 * s.grad.abs().sum(1).max().item()
+    assert t.grad.sum(1).abs().max().item() <= 1e-3 * t.grad.abs().sum(1).max().item()
+    ref = torch.mean(torch.nn.functional.kl_div(torch.log_softmax(s.detach() / 2, 1), torch.softmax(t.detach() / 2, 1),
+                                                reduction="none"))
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-4)
