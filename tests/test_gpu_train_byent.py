@@ -148,7 +148,7 @@ def test_pooled_gemm_full_size_step_matches_gather():
         tr.step(s, w, "head-batch")
         out.append((m.entity_embedding.detach() - init, l_first, tr.loss()))
     (u0, a0, b0), (u1, a1, b1) = out
-    assert abs(a0 - a1) <= 1e-5 * abs(a0) and abs(b0 - b1) <= 1e-4 * abs(b0)
+    assert abs(a0 - a1) <= 5e-5 * abs(a0) and abs(b0 - b1) <= 2e-4 * abs(b0)
     assert u0.abs().max().item() > 0
     assert ((u0 - u1).abs() > 0.05 * u0.abs().max()).float().mean().item() < 1e-3
 
