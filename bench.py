@@ -269,7 +269,8 @@ def run_ours(args):
                                    relations={i: i for i in range(R)}, gamma=gamma).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev, pool=args.pool)
-    topts = {"mode": args.mode, "backward": args.backward, "pooled_gemm": args.pooled_gemm}
+    topts = {"mode": args.mode, "backward": args.backward, "pooled_gemm": args.pooled_gemm,
+             "packed_records": args.packed_records}
     if args.virtual_shards:
         topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
     trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
@@ -470,6 +471,9 @@ def main():
     ap.add_argument("--backward", default="scatter", choices=["scatter", "by_entity"],
                     help="single-GPU backward: scatter = K3 vector REDs + dense Adam (default, the measured path); "
                          "by_entity = atomics-free per-entity backward with Adam fused in (csrc/byent.cu)")
+    ap.add_argument("--packed-records", action="store_true",
+                    help="colpar only: loss sums ride in the all-gathered step records, ONE multi-record backward launch "
+                         "(98 %% efficiency on 2 GPUs; its 4/8-GPU runs timed out in round 1 and await diagnosis)")
     ap.add_argument("--pool", default="independent", choices=["independent", "reference"],
                     help="negative sampler: independent on-device draws (default, the headline) or the reference's "
                          "shared pool of 2K candidates per batch")
