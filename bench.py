@@ -270,7 +270,7 @@ def run_ours(args):
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev, pool=args.pool)
     topts = {"mode": args.mode, "backward": args.backward, "pooled_gemm": args.pooled_gemm,
-             "packed_records": args.packed_records}
+             "packed_records": args.packed_records, "merged_backward": args.merged_backward}
     if args.virtual_shards:
         topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
     trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
@@ -474,6 +474,8 @@ def main():
     ap.add_argument("--packed-records", action="store_true",
                     help="colpar only: loss sums ride in the all-gathered step records, ONE multi-record backward launch "
                          "(98 %% efficiency on 2 GPUs; its 4/8-GPU runs timed out in round 1 and await diagnosis)")
+    ap.add_argument("--merged-backward", action="store_true",
+                    help="colpar only: one backward launch over all G gathered records, collectives unchanged")
     ap.add_argument("--pool", default="independent", choices=["independent", "reference"],
                     help="negative sampler: independent on-device draws (default, the headline) or the reference's "
                          "shared pool of 2K candidates per batch")

@@ -152,7 +152,8 @@ int kge_fused_bwd(const kge_tables_t* tables, int mode, const int64_t* sample, i
  * Multi-record batches: with n_records > 1 the sample / neg / coef_pos / coef_neg / stats pointers
  * describe record 0 and record r lives record_stride_bytes further on (the packed, all-gathered
  * step records of the G ranks); each record holds B positives and the global normaliser is the sum
- * of the records' stats[2]. */
+ * of the records' stats[2].  n_records < -1: |n_records| records whose normaliser is already global —
+ * `stats` is then ONE buffer (e.g. the all-reduced loss sums), not one per record. */
 int kge_fused_bwd_chunk(const kge_tables_t* tables, int mode, const int64_t* sample, int64_t B,
                         const int64_t* neg, int64_t K, const float* coef_pos, const float* coef_neg,
                         const float* stats, const float* grad_loss, int32_t col0, int32_t ncols,

@@ -92,7 +92,7 @@ class DeviceTrainer:
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,
-                 scalar_red=False, backward="scatter", pooled_gemm=False):
+                 scalar_red=False, backward="scatter", pooled_gemm=False, merged_backward=False):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -129,6 +129,9 @@ class DeviceTrainer:
                 self.mode_note = f"colpar unavailable ({type(e).__name__}: {e}); using allreduce"
                 mode = "allreduce"
         self.mode = mode
+        # colpar, opt-in: ONE backward launch over all G gathered records (global stats from the all-reduce)
+        # instead of one launch per source rank; keeps the collectives of the measured default flow
+        self.merged_backward = bool(merged_backward) and mode == "colpar"
         self.pooled_gemm = False
         self.packed_records = bool(packed_records) and mode == "colpar"
         self.ent, self.rel = model.entity_embedding.data, model.relation_embedding.data
@@ -454,6 +457,11 @@ class DeviceTrainer:
             ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s0[:B], n0[:B], mode, cp0[:B], cn0[:B], st0,
                                          self.col0, self.ncols, self.g_ent, self.g_rel, n_records=self.world,
                                          record_stride=self._rec_stride)
+        elif self.ncols > 0 and self.merged_backward and B == self.max_batch:
+            s0, n0, cp0, cn0, _ = self._recs[0]
+            ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s0[:B], n0[:B], mode, cp0[:B], cn0[:B],
+                                         self.stats, self.col0, self.ncols, self.g_ent, self.g_rel,
+                                         n_records=-self.world, record_stride=self._rec_stride)
         elif self.ncols > 0:
             for s_r, n_r, cp_r, cn_r, _ in self._recs:  # the global batch, one source rank at a time
                 ops.fused_backward_chunk_raw(self.spec, self.ent, self.rel, s_r[:B], n_r[:B], mode, cp_r[:B],

@@ -306,6 +306,7 @@ struct BwdParams {
   float* gh_buf;
   float* gt_buf;
   float* gr_buf;
+  int shared_stats;  // multi-record launch whose `stats` is ONE already-global buffer (not one per record)
 };
 
 // Gradient row of an entity from a split id: in the owner's (possibly remote) gradient shard.
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   float scale = 1.f;
   if (p.stats) {
     float wsum = 0.f;
-    for (int r = 0; r < (p.rec_B > 0 ? p.n_rec : 1); ++r)
+    for (int r = 0; r < ((p.rec_B > 0 && !p.shared_stats) ? p.n_rec : 1); ++r)
       wsum += __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p.stats) + (size_t)r * p.rec_stride) + 2);
     scale = (p.grad_loss ? __ldg(p.grad_loss) : 1.f) / (2.f * wsum);
   }
@@ -709,6 +710,10 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   p.grad_rel = grad_rel;
   p.B = (int)B;
   p.K = neg ? (int)K : 0;
+  if (n_records < -1) {  // |n_records| records that share one global stats buffer
+    n_records = -n_records;
+    p.shared_stats = 1;
+  }
   if (n_records > 1) {
     p.rec_B = (int)B;
     p.n_rec = n_records;
@@ -889,7 +894,8 @@ extern "C" int kge_fused_bwd_chunk(const kge_tables_t* t, int mode, const int64_
   if (!sample || !neg || !coef_pos || !coef_neg || !stats || !grad_entity_chunk || !grad_relation_chunk)
     return KGE_E_NULL;
   if (B <= 0 || B > INT32_MAX || K <= 0 || K > INT32_MAX || ncols <= 0) return KGE_E_SIZE;
-  if (n_records < 1 || n_records > 64 || (n_records > 1 && (record_stride_bytes <= 0 || record_stride_bytes % 8)))
+  const int n_abs = n_records < 0 ? -n_records : n_records;
+  if (n_abs < 1 || n_abs > 64 || (n_abs > 1 && (record_stride_bytes <= 0 || record_stride_bytes % 8)))
     return KGE_E_SIZE;
   if (mode != KGE_TAIL_BATCH && mode != KGE_HEAD_BATCH) return KGE_E_MODE;
   return run_bwd(t, mode, sample, B, neg, K, coef_pos, coef_neg, stats, grad_loss, grad_entity_chunk,

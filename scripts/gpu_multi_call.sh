@@ -16,6 +16,8 @@ for cfg in cfg2 cfg4; do
 done
 NCCL_DEBUG=INFO timeout 200 $RUN bench.py --gpus $N --config cfg4 --steps 5 --warmup 3 --mode rowshard \
     > $OUT/nccl_info_${N}gpu.log 2>&1
+timeout 240 $RUN bench.py --gpus $N --config cfg2 --steps 100 --warmup 10 --mode colpar --merged-backward \
+    > $OUT/bench_cfg2_${N}gpu_colpar_merged.json 2> $OUT/bench_cfg2_${N}gpu_colpar_merged.err
 # the packed-records colpar flow (one multi-record backward launch): fine on 2 GPUs, timed out on 4 / 8 in round 1
 NCCL_DEBUG=WARN TORCH_NCCL_DUMP_ON_TIMEOUT=1 timeout 240 $RUN bench.py --gpus $N --config cfg2 --steps 50 --warmup 5 \
     --mode colpar --packed-records > $OUT/bench_cfg2_${N}gpu_colpar_packed.json 2> $OUT/bench_cfg2_${N}gpu_colpar_packed.err

@@ -48,5 +48,5 @@ class Args:
 
 
 Args.backward, Args.virtual_shards, Args.pool, Args.pooled_gemm = backward, int(vshards), pool, gemm == "1"
-Args.packed_records = False
+Args.packed_records = Args.merged_backward = False
 sys.exit(bench.run_ours(Args))

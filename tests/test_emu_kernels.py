@@ -172,6 +172,12 @@ def test_chunked_and_multi_record_backward(model):
     assert np.abs(g2).max() > 0
     _grad_close(g1, g2.astype(np.float64), 1e-6)
     _grad_close(r1, r2.astype(np.float64), 1e-6)
+    # n_records < -1: the same launch with ONE already-global stats buffer (the all-reduced sums)
+    g3, r3 = np.zeros_like(g1), np.zeros_like(r1)
+    H.ok(l.kge_fused_bwd_chunk(C.byref(tb), H.mode_id(mode), p0, B, p0 + o_neg, K, p0 + o_cp, p0 + o_cn, H.P(total), None,
+                               col, wd, -G, rec, H.P(g3), H.P(r3), None))
+    _grad_close(g3, g2.astype(np.float64), 1e-6)
+    _grad_close(r3, r2.astype(np.float64), 1e-6)
 
 
 def test_adam_variants_vs_oracle():
