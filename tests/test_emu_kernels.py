@@ -591,3 +591,94 @@ def test_pooled_dot_step_equals_fused_step_on_the_same_negatives(model, mode, sa
     tb2 = H.tables("RotatE", *ko.init_tables("RotatE", Nn, R, D, gamma, seed=1), gamma)
     assert l.kge_pooled_dot_fwd(C.byref(tb2), 0, H.P(sample), B, H.P(pool), P, H.P(pos_idx), K, H.P(w), 0.5, None, None,
                                 H.P(cpos), H.P(stats), wsp, H.P(lws), None) == -6
+
+
+def _fuzz_cases(n, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        out.append((MODELS + ("pRotatE",))[rng.randint(5)] if True else None)
+    shapes = [(int(rng.choice([1, 2, 7])), int(rng.choice([1, 2, 31, 33, 64, 65])),
+               int(rng.choice([1, 3, 4, 5, 8, 31, 32, 36, 100, 260])), int(rng.choice([1, 2, 5, 40])),
+               int(rng.choice([1, 3])), MODES[rng.randint(2)]) for _ in range(n)]
+    return [(m,) + s for m, s in zip(out, shapes)]
+
+
+@pytest.mark.parametrize("model,B,K,D,Nn,R,mode", _fuzz_cases(36, 123))
+def test_fused_step_edge_shapes(model, B, K, D, Nn, R, mode):
+    """Degenerate and ragged shapes (B = 1, K = 1, D = 1, one entity, partial warps, D just past a vector or
+    block boundary): every route agrees with the oracle, and the specialised paths with the generic one."""
+    l = H.lib()
+    gamma, mod = 6.0, 0.3
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=B * 1000 + K * 10 + D)
+    mk = dict(modulus=mod) if model == "pRotatE" else {}
+    ok_ = dict(modulus=mod) if model == "pRotatE" else {}
+    out = ko.train_step(model, ent, rel, sample, neg, mode, w, gamma=gamma, **ok_)
+    loss, pos, ngs, ge, gr = out[:5]
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, **mk)
+    _close(f["pos"], pos)
+    _close(f["neg"], ngs)
+    assert abs(f["stats"][3] - loss) <= 1e-5 * abs(loss)
+    g_ent, g_rel = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f, **mk)
+    # with one or two entities the contributions of a row can cancel to ~0: compare at the scale of one term
+    floor = max(1e-3, float(np.abs(gr).max()))  # the relation row receives every term with one sign pattern
+    assert np.abs(g_ent - ge).max() <= 1e-4 * max(np.abs(ge).max(), floor)
+    assert np.abs(g_rel - gr).max() <= 1e-4 * max(np.abs(gr).max(), floor)
+    if model == "pRotatE":
+        assert abs(H.modulus_grad(f, gamma, mod) - out[5]) <= 1e-4 * abs(out[5]) + 1e-12
+    if D % 4 == 0:
+        # row shards (more shards than entities included) and the by-entity backward
+        G = 3
+        shards = H.split_rows(ent, G)
+        grads = [np.zeros_like(s) for s in shards]
+        st = H.shards_struct(shards, grads)
+        f1 = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode, shards=st, **mk)
+        for k in f:
+            assert np.array_equal(f[k], f1[k]), k
+        H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f1, shards=st, **mk)
+        assert np.abs(H.merge_rows(grads, Nn) - g_ent).max() <= 1e-6 * max(np.abs(g_ent).max(), floor)
+        p_ref, m_ref, v_ref, g_tmp = ent.copy(), np.zeros_like(ent), np.zeros_like(ent), g_ent.copy()
+        H.ok(l.kge_adam_step(H.P(p_ref), H.P(g_tmp), H.P(m_ref), H.P(v_ref), p_ref.size, 1, 1e-2, 0.9, 0.999, 1e-8, 1, None))
+        p1, m1, v1 = ent.copy(), np.zeros_like(ent), np.zeros_like(ent)
+        r1, rm1, rv1 = rel.copy(), np.zeros_like(rel), np.zeros_like(rel)
+        tb = H.tables(model, p1, r1, gamma, **mk)
+        ws = np.zeros(l.kge_byent_workspace_bytes(C.byref(tb), B, K) + 64, np.uint8)
+        wsp = (ws.ctypes.data + 63) & ~63
+        H.ok(l.kge_bwd_by_entity_adam(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(f["cpos"]),
+                                      H.P(f["cneg"]), H.P(f["stats"]), None, H.P(p1), H.P(m1), H.P(v1), H.P(r1), H.P(rm1),
+                                      H.P(rv1), 1, 1e-2, 0.9, 0.999, 1e-8, wsp, None))
+        np.testing.assert_allclose(m1, m_ref, rtol=1e-4, atol=1e-4 * max(np.abs(g_ent).max(), floor))
+    # top-k of the negative scores and ranks of the whole (tiny) entity set
+    kk = min(K, 3)
+    idx = np.zeros((B, kk), np.int64)
+    H.ok(l.kge_topk_rows(H.P(f["neg"]), B, K, K, kk, H.P(idx), None, None))
+    for r_ in range(B):
+        np.testing.assert_array_equal(idx[r_], np.argsort(-f["neg"][r_].astype(np.float64), kind="stable")[:kk])
+    tb = H.tables(model, ent, rel, gamma, **mk)
+    ranks = np.zeros(B, np.int64)
+    ws = np.zeros(l.kge_rank_workspace_bytes(C.byref(tb), B) + 64, np.uint8)
+    H.ok(l.kge_rank_all(C.byref(tb), H.mode_id(mode), H.P(sample), B, None, H.P(ranks), None, H.P(ws), None))
+    ref, contested = ko.rank_all(model, ent, rel, sample, mode, (np.zeros(0, np.int64),) * 3, (np.zeros(0, np.int64),) * 3,
+                                 gamma=gamma, tie_margin=2e-5, **ok_)
+    assert np.all(np.abs(ranks - ref) <= contested), (ranks, ref)
+
+
+def test_sampler_status_word_on_exhausted_true_sets():
+    """A positive whose true set covers EVERY entity: the independent sampler flags bit 1 (the reference would
+    spin forever), the pool filter flags bit 2 and returns zeros; other rows are unaffected."""
+    l = H.lib()
+    Nn = 3
+    triples = [(0, 0, 0), (0, 0, 1), (0, 0, 2), (1, 0, 2)]  # (h=0, r=0) has every tail; (h=1, r=0) only tail 2
+    tc = ko.build_filter_csr(triples, Nn, "tail")
+    fs = H.csr_struct(tc)
+    sample = np.array([[0, 0, 1], [1, 0, 2]], np.int64)
+    out, status = np.full((2, 4), -1, np.int64), np.zeros(1, np.int32)
+    H.ok(l.kge_sample_negatives(C.byref(fs), 0, H.P(sample), 2, 4, Nn, 7, 0, 1, H.P(out), H.P(status), None))
+    assert status[0] & 2
+    assert set(out[1].tolist()) <= {0, 1}  # tail 2 is filtered for the second positive
+    pool = np.array([2, 1, 2, 0, 2, 2, 1, 2], np.int64)
+    out, pos, status = np.full((2, 4), -1, np.int64), np.full((2, 4), -1, np.int32), np.zeros(1, np.int32)
+    H.ok(l.kge_filter_pool_positions(C.byref(fs), 0, H.P(sample), 2, 4, Nn, H.P(pool), 8, H.P(out), H.P(pos), H.P(status), None))
+    assert status[0] & 4 and not out[0].any() and not pos[0].any()
+    np.testing.assert_array_equal(out[1], [1, 0, 1, 1])  # survivors 1, 0, 1 repeat cyclically
+    np.testing.assert_array_equal(pos[1], [1, 3, 6, 1])
