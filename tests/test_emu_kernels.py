@@ -535,20 +535,21 @@ def test_by_entity_backward_huge_buckets(Nn, B, K):
 
 @pytest.mark.parametrize("model", ("DistMult", "ComplEx"))
 @pytest.mark.parametrize("mode", MODES)
-def test_pooled_dot_step_equals_fused_step_on_the_same_negatives(model, mode, sampler_cases):
+@pytest.mark.parametrize("D,K", [(12, 16), (5, 1), (33, 7)])
+def test_pooled_dot_step_equals_fused_step_on_the_same_negatives(model, mode, D, K, sampler_cases):
     """kge_pooled_dot_fwd/bwd (S = Q·Pool^T and two backward GEMMs; fp32 tiles here, tcgen05 on the GPU)
     == kge_fused_fwd/bwd fed the negatives kge_filter_pool selects from the same pool."""
     l = H.lib()
     g = sampler_cases
     triples = [tuple(int(x) for x in r) for r in g["triples"]]
-    Nn, R, D, K, gamma = int(g["N"]), int(g["R"]), 12, 16, 9.0
+    Nn, R, gamma = int(g["N"]), int(g["R"]), 9.0
     ent, rel = ko.init_tables(model, Nn, R, D, gamma, seed=3)
     ent *= 3.0
     sample = np.ascontiguousarray(g["gen0/sample"], np.int64)
     B = sample.shape[0]
     rng = np.random.RandomState(8)
     w = rng.uniform(0.1, 0.5, B).astype(np.float32)
-    pool = rng.randint(Nn, size=2 * K).astype(np.int64)
+    pool = rng.randint(Nn, size=max(2 * K, 8)).astype(np.int64)
     pool[5] = pool[2]  # a repeated id inside the pool
     P = pool.shape[0]
     csr = ko.build_filter_csr(triples, Nn, "head" if mode == "head-batch" else "tail")
