@@ -10,6 +10,13 @@ cannot parse
 
 and compiles everything except rank_tc.cu (tcgen05/TMA PTX cannot be emulated; kge_rank_all then
 falls back to the fp32 tile kernel, which is what the emulation tests cover).
+
+Memory-safety check of every kernel (out-of-bounds reads and writes on the "device" buffers):
+
+    python tests/emu/build_emu.py --asan          # -> tests/emu/_build_asan/libkge_emu.so
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+    ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1:verify_asan_link_order=0 \
+    KGE_EMU_LIB=tests/emu/_build_asan/libkge_emu.so python -m pytest tests/test_emu_kernels.py -q
 """
 import os
 import re
@@ -178,7 +185,12 @@ def stale():
     return any(os.path.getmtime(f) > t for f in deps)
 
 
-def build(force=False):
+def build(force=False, asan=False):
+    global OUT, LIB
+    if asan:
+        OUT = os.path.join(HERE, "_build_asan")
+        LIB = os.path.join(OUT, "libkge_emu.so")
+        force = True
     if not force and not stale():
         return LIB
     shutil.rmtree(OUT, ignore_errors=True)
@@ -195,6 +207,8 @@ def build(force=False):
     cpps.append(stub)
     flags = ["-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
              "-I", os.path.join(HERE, "include"), "-I", OUT]
+    if asan:
+        flags += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
     procs = []
     for c in cpps:
         o = c[:-4] + ".o"
@@ -206,11 +220,11 @@ def build(force=False):
         if p.returncode != 0:
             raise RuntimeError(f"g++ failed on {c}:\n{log[-4000:]}")
         objs.append(o)
-    subprocess.run(["g++", "-shared", "-o", LIB, *objs], check=True)
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *objs], check=True)
     return LIB
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

@@ -2,6 +2,7 @@
 the host against tests/emu/include/cuda_runtime.h).  Same C ABI, same ctypes prototypes as the product
 binding (mkb_b200/_native.py); "device pointers" are numpy buffers."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -15,7 +16,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        l = C.CDLL(build_emu.build())
+        l = C.CDLL(os.environ.get("KGE_EMU_LIB") or build_emu.build())  # KGE_EMU_LIB: e.g. an ASAN build
         for name, (res, args) in N.PROTOTYPES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
