@@ -25,6 +25,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Order of the `-m gpu` run: the files whose kernels have B200 measurements behind them first, the rows
+# written after the round's GPU budget was spent next, the tcgen05 pooled-GEMM flow (spin-waits on mbarriers)
+# last — so `-x` reports as much as possible before the least-exercised code runs.
+_GPU_FILE_ORDER = ("test_gpu_parity", "test_gpu_multi", "test_gpu_rows_next", "test_gpu_sharded", "test_gpu_train_byent")
+
+
+def pytest_collection_modifyitems(config, items):
+    def key(item):
+        mod = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        rank = _GPU_FILE_ORDER.index(mod) if mod in _GPU_FILE_ORDER else -1  # CPU files keep their place, first
+        return (rank, "pooled_gemm" in item.name)
+
+    items.sort(key=key)  # stable: collection order inside each group is kept
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            # a kernel that never returns must not hold the GPU box until the driver's limit: pytest-timeout's
+            # thread method ends the process (and with it the CUDA context) from a watchdog thread
+            item.add_marker(pytest.mark.timeout(600, method="thread"))
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 

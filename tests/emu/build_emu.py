@@ -116,6 +116,20 @@ def rewrite_extern_shared(text):
                   r"\1* \2 = reinterpret_cast<\1*>(emu::S.dyn_smem);", text)
 
 
+def rewrite_static_shared(text):
+    """``__shared__ T a[n], b;`` -> the same + ``emu::poison_shared(&a, sizeof(a)); ...``: a block starts with
+    garbage in shared memory, not with what the previous block left there."""
+    def fix(m):
+        decl = m.group(0)
+        names = []
+        for d in _split_top(m.group(2)):
+            names.append(re.match(r"\s*(\w+)", d).group(1))
+        return decl + "".join(f" emu::poison_shared(&{n}, sizeof({n}));" for n in names)
+
+    return re.sub(r"(?m)^(\s*__shared__\s+(?:__align__\(\d+\)\s+)?(?:unsigned\s+long\s+long|unsigned\s+int|\w+)\s+)"
+                  r"([^;()]+);", fix, text)
+
+
 def rewrite_asm(text):
     out, pos = [], 0
     for m in re.finditer(r"\basm\s*(?:volatile\s*)?\(", text):
@@ -141,7 +155,8 @@ def rewrite_asm(text):
         ins = [e for c, e in ops if not c.startswith("=")]
         if re.match(r"red\.relaxed\.(gpu|sys)\.global\.add\.v4\.f32", ptx):
             p, v = ins[0], ins[1:5]
-            code = "{ float* _p = (float*)(" + p + "); " + " ".join(f"_p[{i}] += ({e});" for i, e in enumerate(v)) + " }"
+            code = "{ float* _p = (float*)(" + p + "); if ((uintptr_t)_p & 15) { fprintf(stderr, \"cuda_emu: misaligned " \
+                   "red.v4.f32\\n\"); abort(); } " + " ".join(f"_p[{i}] += ({e});" for i, e in enumerate(v)) + " }"
         elif re.match(r"red\.relaxed\.(gpu|sys)\.global\.add\.f32", ptx):
             code = f"{{ *(float*)({ins[0]}) += ({ins[1]}); }}"
         elif ptx.startswith("sqrt.approx"):
@@ -160,7 +175,7 @@ def rewrite_asm(text):
 def preprocess(name):
     text = open(os.path.join(CSRC, name)).read()
     text = text.replace('#include "../../include/kge_b200.h"', f'#include "{os.path.join(ROOT, "include", "kge_b200.h")}"')
-    text = rewrite_asm(rewrite_extern_shared(rewrite_launches(text)))
+    text = rewrite_asm(rewrite_static_shared(rewrite_extern_shared(rewrite_launches(text))))
     return f"// GENERATED by tests/emu/build_emu.py from mkb_b200/csrc/{name} — do not edit\n" + text
 
 
@@ -208,7 +223,9 @@ def build(force=False, asan=False):
     flags = ["-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
              "-I", os.path.join(HERE, "include"), "-I", OUT]
     if asan:
-        flags += ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
+        # + UBSan: misaligned vector / 64-bit accesses fault on the device, signed overflow is an indexing bug
+        flags += ["-g", "-fsanitize=address,alignment,signed-integer-overflow,shift,bounds",
+                  "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"]
     procs = []
     for c in cpps:
         o = c[:-4] + ".o"
@@ -220,7 +237,7 @@ def build(force=False, asan=False):
         if p.returncode != 0:
             raise RuntimeError(f"g++ failed on {c}:\n{log[-4000:]}")
         objs.append(o)
-    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if asan else []), "-o", LIB, *objs], check=True)
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if asan else []), "-o", LIB, *objs], check=True)
     return LIB
 
 

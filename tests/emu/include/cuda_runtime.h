@@ -66,7 +66,14 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp {
   int multiProcessorCount, major, minor;
 };
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+namespace emu {
+inline cudaError_t last_error = 0;  // set by emu::launch when a launch configuration breaks a CUDA limit
+}
+inline cudaError_t cudaGetLastError() {
+  const cudaError_t e = emu::last_error;
+  emu::last_error = 0;
+  return e;
+}
 inline cudaError_t cudaGetDevice(int* d) {
   *d = 0;
   return cudaSuccess;
@@ -85,7 +92,9 @@ template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
   return cudaSuccess;
 }
-inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+inline const char* cudaGetErrorString(cudaError_t e) {
+  return e == 9 ? "invalid configuration argument (emulated)" : "emulated CUDA error";
+}
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
   memset(p, v, n);
   return cudaSuccess;
@@ -103,7 +112,35 @@ struct Warp {
   int live, count;
   unsigned gen;
   unsigned long long slot[32];
+  int site[32];  // source line of the warp primitive each lane is waiting in
 };
+// Schedule perturbation (race check).  Fibers switch only at barriers / shuffles, so a fixed thread order hides
+// every missing __syncthreads whose reader happens to run after its writer.  KGE_EMU_ORDER=reverse|random runs
+// the threads of a block (and the blocks of a grid) in the opposite / a shuffled order: a kernel without data
+// races produces the same result under all three; KGE_EMU_SEED seeds the shuffle.
+struct Config {
+  int order = 0;  // 0 forward, 1 reverse, 2 random
+  unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  Config() {
+    const char* o = getenv("KGE_EMU_ORDER");
+    if (o && !strcmp(o, "reverse")) order = 1;
+    if (o && !strcmp(o, "random")) order = 2;
+    if (const char* sd = getenv("KGE_EMU_SEED")) rng ^= strtoull(sd, nullptr, 10) * 0xD1342543DE82EF95ull;
+  }
+  unsigned next() {  // splitmix64
+    unsigned long long z = (rng += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (unsigned)((z ^ (z >> 31)) >> 16);
+  }
+  void permute(std::vector<int>& v) {
+    if (order == 1) std::reverse(v.begin(), v.end());
+    if (order == 2)
+      for (size_t i = v.size(); i > 1; --i) std::swap(v[i - 1], v[next() % i]);
+  }
+};
+inline Config C;
+
 struct State {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
@@ -117,6 +154,8 @@ struct State {
   dim3 block_dim, grid_dim;
   std::vector<char> dyn;
   void* dyn_smem = nullptr;
+  size_t dyn_bytes = 0;
+  std::vector<void*> poisoned;  // static __shared__ objects already poisoned for the running block
   long launches = 0;
 };
 inline State S;
@@ -166,11 +205,27 @@ inline void run_block(int nthreads) {
     f.ctx.uc_link = &S.sched;
     makecontext(&f.ctx, (void (*)())entry, 0);
   }
+  // shared memory holds garbage when a block starts: poison it so reads of unwritten words show (NaN / -1)
+  if (S.dyn_bytes) memset(S.dyn_smem, 0xFF, S.dyn_bytes);
+  S.poisoned.clear();
+  std::vector<int> order(nthreads);
+  for (int t = 0; t < nthreads; ++t) order[t] = t;
+  C.permute(order);
   long spins = 0;
   while (S.live > 0) {
-    for (int t = 0; t < nthreads; ++t) {
+    if (C.order == 2 && spins) C.permute(order);
+    // random mode: warps (and lanes) also advance at different RATES — half of the warps and a quarter of the
+    // remaining lanes sit a round out, so warps drift apart as far as the barriers allow
+    unsigned skip_warp = 0, skip_lane = 0;
+    if (C.order == 2) {
+      skip_warp = C.next();
+      skip_lane = C.next() & C.next();
+    }
+    for (int oi = 0; oi < nthreads; ++oi) {
+      const int t = order[oi];
       Fiber& f = S.fibers[t];
       if (f.done) continue;
+      if (C.order == 2 && (((skip_warp >> (f.warp & 31)) & 1u) || ((skip_lane >> f.lane) & 1u))) continue;
       S.cur = &f;
       swapcontext(&S.sched, &f.ctx);
     }
@@ -184,19 +239,50 @@ inline void run_block(int nthreads) {
 
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F&& body) {
+  // the launch limits of sm_100 (cudaErrorInvalidConfiguration = 9 on the device; here too, and nothing runs)
+  const unsigned long long nthreads_ll = (unsigned long long)block.x * block.y * block.z;
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0 || nthreads_ll == 0 || nthreads_ll > 1024 || block.x > 1024 ||
+      block.y > 1024 || block.z > 64 || grid.x > 2147483647u || grid.y > 65535u || grid.z > 65535u ||
+      smem > 232448) {
+    fprintf(stderr, "cuda_emu: invalid launch configuration grid=(%u,%u,%u) block=(%u,%u,%u) smem=%zu\n", grid.x,
+            grid.y, grid.z, block.x, block.y, block.z, smem);
+    last_error = 9;
+    return;
+  }
   S.grid_dim = grid;
   S.block_dim = block;
   S.dyn.assign(smem + 64, 0);
   S.dyn_smem = (void*)(((uintptr_t)S.dyn.data() + 63) & ~(uintptr_t)63);
+  S.dyn_bytes = smem;
   S.body = body;
   ++S.launches;
-  const int nthreads = (int)(block.x * block.y * block.z);
-  for (unsigned z = 0; z < grid.z; ++z)
-    for (unsigned y = 0; y < grid.y; ++y)
-      for (unsigned x = 0; x < grid.x; ++x) {
-        S.block_idx = uint3{x, y, z};
-        run_block(nthreads);
-      }
+  const int nthreads = (int)nthreads_ll;
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  if (C.order == 0) {
+    for (unsigned z = 0; z < grid.z; ++z)
+      for (unsigned y = 0; y < grid.y; ++y)
+        for (unsigned x = 0; x < grid.x; ++x) {
+          S.block_idx = uint3{x, y, z};
+          run_block(nthreads);
+        }
+  } else {  // blocks of a grid have no guaranteed order either
+    std::vector<int> border((size_t)nblocks);
+    for (size_t b = 0; b < border.size(); ++b) border[b] = (int)b;
+    C.permute(border);
+    for (int b : border) {
+      S.block_idx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / (grid.x * grid.y))};
+      run_block(nthreads);
+    }
+  }
+}
+
+// static __shared__ objects (build_emu.py appends a call after each declaration): first fiber of a block to
+// reach the declaration fills it with 0xFF
+inline void poison_shared(void* p, size_t n) {
+  for (void* q : S.poisoned)
+    if (q == p) return;
+  S.poisoned.push_back(p);
+  memset(p, 0xFF, n);
 }
 
 inline void warp_barrier() {
@@ -209,14 +295,42 @@ inline void warp_barrier() {
     while (w.gen == my) yield();
   }
 }
+// Every lane named in `mask` must execute the SAME primitive (undefined behaviour on the device otherwise):
+// the calling lane has to be in the mask, every live lane of the warp has to be in it (this emulation
+// rendezvouses all live lanes), and all lanes must have come from the same source line.
+inline void check_site(unsigned mask, int line) {
+  Warp& w = S.warps[S.cur->warp];
+  const int wi = S.cur->warp;
+  if (!((mask >> S.cur->lane) & 1u)) {
+    fprintf(stderr, "cuda_emu: lane %d calls a *_sync primitive (line %d) with mask %08x that excludes it\n",
+            S.cur->lane, line, mask);
+    abort();
+  }
+  for (int l = 0; l < 32; ++l) {
+    const int t = wi * 32 + l;
+    if (t >= (int)S.fibers.size() || S.fibers[t].done) continue;
+    if (!((mask >> l) & 1u)) {
+      fprintf(stderr, "cuda_emu: *_sync primitive at line %d: live lane %d is not in mask %08x (partial masks are "
+                      "not emulated)\n", line, l, mask);
+      abort();
+    }
+    if (w.site[l] != line) {
+      fprintf(stderr, "cuda_emu: divergent warp primitive: lane %d is at line %d, lane %d at line %d\n",
+              S.cur->lane, line, l, w.site[l]);
+      abort();
+    }
+  }
+}
 template <class T>
-inline T warp_exchange(T v, int src_lane) {
+inline T warp_exchange(T v, int src_lane, unsigned mask, int line) {
   static_assert(sizeof(T) <= 8, "shuffle of a type wider than 8 bytes");
   Warp& w = S.warps[S.cur->warp];
   unsigned long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
   w.slot[S.cur->lane] = raw;
+  w.site[S.cur->lane] = line;
   warp_barrier();
+  check_site(mask, line);
   raw = w.slot[src_lane & 31];
   warp_barrier();  // nobody overwrites a slot before every lane has read
   T out;
@@ -244,28 +358,30 @@ inline void __syncthreads() {
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 inline void __threadfence() {}
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src) {
-  return emu::warp_exchange(v, src);
+inline T __shfl_sync(unsigned mask, T v, int src, int line = __builtin_LINE()) {
+  return emu::warp_exchange(v, src, mask, line);
 }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
-  return emu::warp_exchange(v, emu::S.cur->lane ^ lane_mask);
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int line = __builtin_LINE()) {
+  return emu::warp_exchange(v, emu::S.cur->lane ^ lane_mask, mask, line);
 }
 template <class T>
-inline T __shfl_down_sync(unsigned, T v, int delta) {
+inline T __shfl_down_sync(unsigned mask, T v, int delta, int line = __builtin_LINE()) {
   const int src = emu::S.cur->lane + delta;
-  return emu::warp_exchange(v, src < 32 ? src : emu::S.cur->lane);
+  return emu::warp_exchange(v, src < 32 ? src : emu::S.cur->lane, mask, line);
 }
 template <class T>
-inline T __shfl_up_sync(unsigned, T v, int delta) {
+inline T __shfl_up_sync(unsigned mask, T v, int delta, int line = __builtin_LINE()) {
   const int src = emu::S.cur->lane - delta;
-  return emu::warp_exchange(v, src >= 0 ? src : emu::S.cur->lane);
+  return emu::warp_exchange(v, src >= 0 ? src : emu::S.cur->lane, mask, line);
 }
-inline unsigned __ballot_sync(unsigned, int pred) {
+inline unsigned __ballot_sync(unsigned mask, int pred, int line = __builtin_LINE()) {
   using namespace emu;
   Warp& w = S.warps[S.cur->warp];
   w.slot[S.cur->lane] = pred ? 1ull : 0ull;
+  w.site[S.cur->lane] = line;
   warp_barrier();
+  check_site(mask, line);
   unsigned m = 0;
   for (int l = 0; l < 32; ++l) {
     const int t = S.cur->warp * 32 + l;

