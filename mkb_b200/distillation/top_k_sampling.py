@@ -1,0 +1,113 @@
+"""``TopKSampling`` — mirror of mkb/distillation/top_k_sampling.py:321-677.
+
+For every training triple the reference scores ALL shared entities as head candidates, all shared
+relations, and all shared entities as tail candidates with the teacher, argsorts each score row and
+keeps the first ``batch_size_entity`` / ``batch_size_relation`` positions (``_get_rank_entities`` :672-677,
+``_get_rank_relations`` :665-669) — a Python loop over the batch with three model calls and three full
+sorts per triple (:577-604).  Here the whole batch is three kernel calls per candidate chunk:
+``kge_score_fwd`` over ``[B, n_candidates]`` (head-batch, tail-batch) and over the 3-D ``[B, n_relations, 3]``
+sample, each followed by ``kge_topk_rows`` (exact radix select, ties by candidate order = a stable
+descending argsort).  The random entities / relations appended afterwards consume the seeded
+``numpy.RandomState`` exactly like ``_randomize_distribution`` (:877-960).
+"""
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+import torch
+
+from .. import ops
+
+__all__ = ["TopKSampling"]
+
+
+class TopKSampling:
+    """Same constructor as the reference (:486-499).  ``get(sample, teacher)`` returns the six int64 tensors
+    ``(head_teacher, relation_teacher, tail_teacher, head_student, relation_student, tail_student)`` of shape
+    ``[B, batch_size_entity]`` / ``[B, batch_size_relation]`` on the teacher's device."""
+
+    def __init__(self, teacher_entities, teacher_relations, student_entities, student_relations, batch_size_entity,
+                 batch_size_relation, n_random_entities, n_random_relations, device="cpu", seed=None, **kwargs):
+        self.batch_size_entity_top_k = batch_size_entity
+        self.batch_size_relation_top_k = batch_size_relation
+        self.n_random_entities = n_random_entities
+        self.n_random_relations = n_random_relations
+        self.device = device
+        self._rng = np.random.RandomState(seed)
+        self.mapping_entities = collections.OrderedDict(
+            {i: student_entities[e] for e, i in teacher_entities.items() if e in student_entities})
+        self.mapping_relations = collections.OrderedDict(
+            {i: student_relations[r] for r, i in teacher_relations.items() if r in student_relations})
+        i64 = torch.int64
+        self.entities_teacher_selection = torch.tensor(list(self.mapping_entities.keys()), dtype=i64)
+        self.entities_teacher_prediction = self.entities_teacher_selection.view(1, -1)
+        self.entities_student = torch.tensor(list(self.mapping_entities.values()), dtype=i64)
+        self.relations_teacher = torch.tensor(list(self.mapping_relations.keys()), dtype=i64)
+        self.relations_student = torch.tensor(list(self.mapping_relations.values()), dtype=i64)
+        self._dev_cache = None
+
+    @property
+    def supervised(self):
+        """Do not include the ground truth (:551-554)."""
+        return False
+
+    @property
+    def batch_size_entity(self):
+        return self.batch_size_entity_top_k + self.n_random_entities
+
+    @property
+    def batch_size_relation(self):
+        return self.batch_size_relation_top_k + self.n_random_relations
+
+    def _on(self, dev):
+        if self._dev_cache is None or self._dev_cache[0] != dev:
+            self._dev_cache = (dev, self.entities_teacher_selection.to(dev), self.entities_student.to(dev),
+                               self.relations_teacher.to(dev), self.relations_student.to(dev))
+        return self._dev_cache[1:]
+
+    def get(self, sample, teacher, max_ids_per_call=1 << 24, **kwargs):
+        dev = teacher.entity_embedding.device
+        ent_t, ent_s, rel_t, rel_s = self._on(dev)
+        sample = sample.to(dev)
+        B, n_ent, n_rel = sample.shape[0], ent_t.shape[0], rel_t.shape[0]
+        k_e = min(int(self.batch_size_entity_top_k), n_ent)  # argsort(...)[:, :k] never returns more than exist
+        k_r = min(int(self.batch_size_relation_top_k), n_rel)
+        rank_h = torch.empty((B, k_e), dtype=torch.int64, device=dev)
+        rank_t = torch.empty((B, k_e), dtype=torch.int64, device=dev)
+        rank_r = torch.empty((B, k_r), dtype=torch.int64, device=dev)
+        training = teacher.training
+        teacher.eval()
+        with torch.no_grad():
+            step = max(1, int(max_ids_per_call) // max(n_ent, 1))  # bound the [b, n_candidates] id matrix
+            for lo in range(0, B, step):
+                s = sample[lo:lo + step]
+                b = s.shape[0]
+                cand = ent_t.view(1, -1).expand(b, n_ent).contiguous()
+                if k_e:
+                    rank_h[lo:lo + b] = ops.topk_rows(teacher(s, cand, "head-batch"), k_e)
+                    rank_t[lo:lo + b] = ops.topk_rows(teacher(s, cand, "tail-batch"), k_e)
+                if k_r:
+                    rels = torch.stack([s[:, 0:1].expand(b, n_rel), rel_t.view(1, -1).expand(b, n_rel),
+                                        s[:, 2:3].expand(b, n_rel)], dim=2).contiguous()  # [b, n_rel, 3]
+                    rank_r[lo:lo + b] = ops.topk_rows(teacher(rels), k_r)
+        if training:
+            teacher.train()
+        head_teacher, head_student = ent_t[rank_h], ent_s[rank_h]
+        tail_teacher, tail_student = ent_t[rank_t], ent_s[rank_t]
+        # the reference indexes relations_student for BOTH relation outputs (:604-607); kept
+        relation_teacher, relation_student = rel_s[rank_r], rel_s[rank_r]
+
+        if self.n_random_entities > 0:  # _randomize_distribution :894-925, same RNG consumption
+            rnd_t = self._rng.choice(list(self.mapping_entities.keys()), size=self.n_random_entities, replace=False)
+            rnd_s = torch.tensor([[self.mapping_entities[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            head_teacher, head_student = torch.cat([head_teacher, rnd_t], 1), torch.cat([head_student, rnd_s], 1)
+            tail_teacher, tail_student = torch.cat([tail_teacher, rnd_t], 1), torch.cat([tail_student, rnd_s], 1)
+        if self.n_random_relations > 0:  # :927-949
+            rnd_t = self._rng.choice(list(self.mapping_relations.keys()), size=self.n_random_relations, replace=False)
+            rnd_s = torch.tensor([[self.mapping_relations[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            relation_teacher = torch.cat([relation_teacher, rnd_t], 1)
+            relation_student = torch.cat([relation_student, rnd_s], 1)
+        return (head_teacher, relation_teacher, tail_teacher, head_student, relation_student, tail_student)

@@ -145,7 +145,7 @@ struct State {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   std::vector<char> stacks;
-  int live = 0, bar_count = 0;
+  int live = 0, bar_count = 0, bar_site = 0;
   unsigned bar_gen = 0;
   ucontext_t sched;
   Fiber* cur = nullptr;
@@ -345,9 +345,16 @@ inline T warp_exchange(T v, int src_lane, unsigned mask, int line) {
 #define blockDim (emu::S.block_dim)
 #define gridDim (emu::S.grid_dim)
 
-inline void __syncthreads() {
+inline void __syncthreads(int line = __builtin_LINE()) {
   using namespace emu;
   const unsigned my = S.bar_gen;
+  // every thread of the block must reach the SAME barrier (a barrier in divergent code is undefined on the device)
+  if (S.bar_count == 0) S.bar_site = line;
+  else if (S.bar_site != line) {
+    fprintf(stderr, "cuda_emu: block (%u,%u): threads wait at different __syncthreads (lines %d and %d)\n",
+            S.block_idx.x, S.block_idx.y, S.bar_site, line);
+    abort();
+  }
   if (++S.bar_count >= S.live) {
     S.bar_count = 0;
     ++S.bar_gen;

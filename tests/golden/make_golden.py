@@ -472,10 +472,51 @@ def gen_loader_order():
     print("loader_order", len(out))
 
 
+def gen_distill_rows():
+    """TopKSampling.get of the reference (distillation/top_k_sampling.py:564-660) on two small KGs whose
+    label sets overlap only partly, for a RotatE and a TransE teacher; stored: tables, label maps, outputs."""
+    from mkb import distillation
+
+    out = {}
+    rng = np.random.RandomState(9)
+    Nt, Ns, Rt, Rs, D = 60, 50, 7, 5, 8
+    labels_t = [f"e{i}" for i in rng.permutation(80)[:Nt]]
+    labels_s = [f"e{i}" for i in rng.permutation(80)[:Ns]]
+    rl_t = [f"r{i}" for i in rng.permutation(9)[:Rt]]
+    rl_s = [f"r{i}" for i in rng.permutation(9)[:Rs]]
+    ent_t = {e: i for i, e in enumerate(labels_t)}
+    ent_s = {e: i for i, e in enumerate(labels_s)}
+    rel_t = {r: i for i, r in enumerate(rl_t)}
+    rel_s = {r: i for i, r in enumerate(rl_s)}
+    out["labels_t"], out["labels_s"] = np.array(labels_t), np.array(labels_s)
+    out["rl_t"], out["rl_s"] = np.array(rl_t), np.array(rl_s)
+    sample = torch.tensor(np.stack([rng.randint(Nt, size=6), rng.randint(Rt, size=6), rng.randint(Nt, size=6)], 1))
+    out["sample"] = _np(sample)
+    for name in ("RotatE", "TransE", "ComplEx"):
+        torch.manual_seed(3)
+        teacher = getattr(models, name)(hidden_dim=D, entities=ent_t, relations=rel_t, gamma=6)
+        with torch.no_grad():
+            teacher.entity_embedding.mul_(3.0)
+        out[f"{name}/ent"], out[f"{name}/rel"] = _np(teacher.entity_embedding), _np(teacher.relation_embedding)
+        for tag, (ke, kr, ne, nr) in {"a": (4, 2, 2, 1), "b": (7, 3, 0, 0)}.items():
+            smp = distillation.TopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                            student_relations=rel_s, batch_size_entity=ke, batch_size_relation=kr,
+                                            n_random_entities=ne, n_random_relations=nr, seed=42)
+            for call in range(2):  # two calls: the RNG stream continues
+                res = smp.get(sample=sample, teacher=teacher)
+                for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
+                    out[f"{name}/{tag}/{call}/{k}"] = _np(t)
+            assert teacher.training
+    np.savez_compressed(os.path.join(HERE, "distill_rows.npz"), **out)
+    print("distill_rows", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next"]
+    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next", "distill"]
     if "next" in which:
         gen_next_rows()
+    if "distill" in which:
+        gen_distill_rows()
     if "loader" in which:
         gen_loader_order()
     if "step" in which:

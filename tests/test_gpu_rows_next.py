@@ -260,3 +260,31 @@ def test_triplet_classification_matches_reference(g, model):
     assert abs(thr - ref) <= 1e-4 * max(abs(ref), 1.0)
     acc = evaluation.accuracy(model=m, X=X, y=y, threshold=ref, batch_size=8, device=DEV)
     assert abs(acc - float(g[f"{model}/accuracy"])) <= 1.0 / len(X) + 1e-9
+
+
+# --------------------------------------------------------------------------------------------------
+# distillation.TopKSampling: score all shared candidates with the teacher, keep the k best, append random ones
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ("RotatE", "TransE", "ComplEx"))
+def test_top_k_sampling_matches_reference(model):
+    from mkb_b200 import distillation
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = getattr(models, model)(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6)
+    teacher._set_params(torch.from_numpy(d[f"{model}/ent"].copy()), torch.from_numpy(d[f"{model}/rel"].copy()))
+    teacher = teacher.to(DEV)
+    sample = torch.from_numpy(d["sample"])
+    for tag, (ke, kr, ne, nr) in {"a": (4, 2, 2, 1), "b": (7, 3, 0, 0)}.items():
+        smp = distillation.TopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                        student_relations=rel_s, batch_size_entity=ke, batch_size_relation=kr,
+                                        n_random_entities=ne, n_random_relations=nr, seed=42)
+        assert (smp.batch_size_entity, smp.batch_size_relation, smp.supervised) == (ke + ne, kr + nr, False)
+        for call in range(2):
+            got = smp.get(sample=sample, teacher=teacher, max_ids_per_call=100 if call else 1 << 24)  # chunked too
+            for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), got):
+                np.testing.assert_array_equal(t.cpu().numpy(), d[f"{model}/{tag}/{call}/{k}"], err_msg=f"{tag}/{call}/{k}")
+        assert teacher.training

@@ -329,3 +329,28 @@ def test_classification_threshold_matches_sklearn_and_reference(next_rows):
         assert abs(thr - float(g[f"{name}/threshold"])) <= 1e-4 * abs(thr)
         acc = evaluation.accuracy(model=m, X=X, y=y, threshold=float(g[f"{name}/threshold"]), batch_size=8, device="cpu")
         assert abs(acc - float(g[f"{name}/accuracy"])) <= 1.0 / len(X) + 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------
+# bundled-dataset wrappers (they read mkb's own data directory; nothing is redistributed here)
+# ---------------------------------------------------------------------------------------------------
+_REF_DATA = "/root/reference/mkb/datasets"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(_REF_DATA, "wn18rr", "train.csv")), reason="mkb data not present")
+def test_bundled_dataset_wrappers(monkeypatch):
+    from mkb_b200 import datasets
+
+    monkeypatch.setenv("MKB_DATASETS", _REF_DATA)
+    ds = datasets.Wn18rr(batch_size=256, shuffle=False, seed=42)
+    assert (len(ds.entities), len(ds.relations)) == (40943, 11)  # mkb/datasets/wn18rr.py:44-49
+    assert (len(ds.train), len(ds.valid), len(ds.test)) == (86835, 3034, 3134)
+    assert len(ds.classification_valid["X"]) == len(ds.classification_valid["y"]) == 2 * len(ds.valid)
+    assert ds.name == "Wn18rr" and "Train triples  86835" in repr(ds)
+    b = next(iter(ds))
+    assert b["sample"].shape == (256, 3) and b["mode"] == "head-batch"
+    fb = datasets.Fb15k237(batch_size=1024, path=os.path.join(_REF_DATA, "fb15k237"))
+    assert (len(fb.entities), len(fb.relations), len(fb.train)) == (14541, 237, 272115)
+    monkeypatch.delenv("MKB_DATASETS")
+    with pytest.raises(FileNotFoundError, match="MKB_DATASETS"):
+        datasets.Yago310(batch_size=8, path="/nonexistent")
