@@ -7,7 +7,7 @@ Same public surface as the reference for the path it covers::
 Everything numeric runs in ``libkge_b200.so`` (hand-written CUDA behind the C ABI declared in
 ``include/kge_b200.h``); there is no CPU fallback.
 """
-from . import compose, datasets, evaluation, losses, models, optim, ops, sampling, utils  # noqa: F401
+from . import compose, datasets, distillation, evaluation, losses, models, optim, ops, sampling, utils  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["compose", "datasets", "evaluation", "losses", "models", "optim", "ops", "sampling", "utils"]
+__all__ = ["compose", "datasets", "distillation", "evaluation", "losses", "models", "optim", "ops", "sampling", "utils"]

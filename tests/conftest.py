@@ -39,7 +39,7 @@ def pytest_collection_modifyitems(config, items):
 
     items.sort(key=key)  # stable: collection order inside each group is kept
     for item in items:
-        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout") and not EMU:
             # a kernel that never returns must not hold the GPU box until the driver's limit: pytest-timeout's
             # thread method ends the process (and with it the CUDA context) from a watchdog thread
             item.add_marker(pytest.mark.timeout(600, method="thread"))

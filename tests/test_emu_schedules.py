@@ -1,0 +1,27 @@
+"""Race check of the kernels on the CUDA emulation (tests/emu): the emulation suite must give the same
+answers when the threads of a block and the blocks of a grid run in the opposite order and in shuffled
+orders with warps advancing at different rates (KGE_EMU_ORDER, tests/emu/include/cuda_runtime.h) — a
+missing barrier or an inter-block ordering assumption shows up as a wrong result.  Shared memory is
+poisoned at every block start and launch configurations are checked against the sm_100 limits in every
+mode.  The schedule is fixed when the emulation library is loaded, so each order runs in its own process."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+SUBSET = ("test_fused_step_vs_oracle or test_sharded_kernels_equal_unsharded or test_chunked_and_multi_record or "
+          "test_samplers_bit_exact or test_topk_rows or test_kl_divergence or test_by_entity or test_pooled_dot or "
+          "test_protate_fused or test_rank_tile or test_sharded_rank_counts or test_unfused_loss")
+
+
+@pytest.mark.parametrize("order,seed", [("reverse", 0), ("random", 1), ("random", 2)])
+def test_emulation_suite_is_schedule_independent(order, seed):
+    env = dict(os.environ, KGE_EMU_ORDER=order, KGE_EMU_SEED=str(seed))
+    env.pop("KGE_TEST_EMU", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emu_kernels.py"), "-q", "-x",
+                        "-p", "no:cacheprovider", "-k", SUBSET], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -354,3 +354,33 @@ def test_bundled_dataset_wrappers(monkeypatch):
     monkeypatch.delenv("MKB_DATASETS")
     with pytest.raises(FileNotFoundError, match="MKB_DATASETS"):
         datasets.Yago310(batch_size=8, path="/nonexistent")
+
+
+# ---------------------------------------------------------------------------------------------------
+# distillation.TopKSampling host logic (candidate maps, batching / chunking, RNG consumption): the kernels
+# are replaced by the oracle scorer and a stable argsort, the outputs are the reference's own
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ("RotatE", "TransE", "ComplEx"))
+def test_top_k_sampling_host_logic_matches_reference(name, monkeypatch):
+    from conftest import load_golden
+    from mkb_b200 import distillation, ops
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = _OracleModel(name, d[f"{name}/ent"].astype(np.float64), d[f"{name}/rel"].astype(np.float64), 6.0)
+    teacher.entity_embedding = torch.zeros(1)  # only its .device is read
+    monkeypatch.setattr(ops, "topk_rows", lambda s, k: torch.from_numpy(
+        np.argsort(-s.numpy().astype(np.float64), axis=1, kind="stable")[:, :k].copy()))
+    sample = torch.from_numpy(d["sample"])
+    for tag, (ke, kr, ne, nr) in {"a": (4, 2, 2, 1), "b": (7, 3, 0, 0)}.items():
+        smp = distillation.TopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                        student_relations=rel_s, batch_size_entity=ke, batch_size_relation=kr,
+                                        n_random_entities=ne, n_random_relations=nr, seed=42)
+        for call in range(2):
+            got = smp.get(sample=sample, teacher=teacher, max_ids_per_call=100 if call else 1 << 24)
+            for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), got):
+                np.testing.assert_array_equal(t.numpy(), d[f"{name}/{tag}/{call}/{k}"], err_msg=f"{tag}/{call}/{k}")
+        assert teacher.training
