@@ -43,13 +43,15 @@ class _RollingMean:
 
 class Pipeline:
     def __init__(self, epochs, eval_every=2000, early_stopping_rounds=3, device="cpu", fused=True,
-                 loss_every=1, trainer_options=None):
+                 loss_every=1, trainer_options=None, adopt_torch_adam=True):
         """``fused=False`` forces the generic three-call loop.  ``loss_every`` > 1 reads the loss back
         to the host only every that many steps (the reference's ``error.item()`` at pipeline.py:242 is
         a device sync per step); 1 keeps the reference behaviour.  ``trainer_options`` are keyword
         arguments for the device-resident ``DeviceTrainer`` (e.g. ``{"mode": "rowshard"}`` to row-shard
-        the entity table over the GPUs of the process group)."""
+        the entity table over the GPUs of the process group).  ``adopt_torch_adam=False`` keeps a stock
+        ``torch.optim.Adam`` stepping through autograd instead of being taken over by the device-resident step."""
         self.trainer_options = dict(trainer_options or {})
+        self.adopt_torch_adam = bool(adopt_torch_adam)
         self.epochs = epochs
         self.eval_every = eval_every
         self.early_stopping_rounds = early_stopping_rounds
@@ -67,13 +69,34 @@ class Pipeline:
     def _can_fuse(self, model, loss):
         return self.fused and isinstance(model, BaseModel) and type(loss) is Adversarial
 
+    @staticmethod
+    def _plain_torch_adam(optimizer):
+        """torch.optim.Adam exactly as the reference's quick-start builds it (README.md:123-126): the update the
+        device-resident step applies (kge_adam_step is torch.optim.Adam's rule, tested against it)."""
+        if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        return (not g.get("amsgrad", False) and g.get("weight_decay", 0) == 0 and not g.get("maximize", False)
+                and not g.get("capturable", False) and not g.get("differentiable", False)
+                and not g.get("decoupled_weight_decay", False) and not torch.is_tensor(g["lr"]))
+
     def _device_trainer(self, model, dataset, sampling, optimizer, loss):
-        """The whole step can stay on the device when every piece is ours: fused-capable (model, loss),
-        this package's sampler and ``optim.DenseAdam`` over the model's parameters (one param group)."""
-        if not (self._can_fuse(model, loss) and isinstance(optimizer, DenseAdam)
+        """The whole step can stay on the device when every piece is known: fused-capable (model, loss), this
+        package's sampler, and dense Adam over the model's parameters in one param group — ``optim.DenseAdam``
+        or a stock ``torch.optim.Adam`` (``adopt_torch_adam``), whose hyper-parameters and moments are taken
+        over and kept current in ``optimizer.state``."""
+        ours = isinstance(optimizer, DenseAdam) or (self.adopt_torch_adam and self._plain_torch_adam(optimizer))
+        if not (self._can_fuse(model, loss) and ours
                 and isinstance(sampling, NegativeSampling) and len(optimizer.param_groups) == 1
                 and model.entity_embedding.is_cuda):
             return None
+        # any OTHER trainable parameter with a gradient would be skipped by the device step
+        listed = [p for p in optimizer.param_groups[0]["params"]
+                  if p is not model.entity_embedding and p is not model.relation_embedding]
+        if any(p.grad is not None for p in listed):
+            return None
+        if model.kernel_modulus is not None and not isinstance(optimizer, DenseAdam):
+            return None  # pRotatE's trainable modulus keeps its moments inside the trainer
         # the fused forward keeps the query and the K scores of a positive in one CTA's shared memory
         if (model.entity_dim + 3 + int(sampling.size)) * 4 > 200 * 1024:
             return None

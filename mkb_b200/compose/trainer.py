@@ -71,8 +71,11 @@ class DeviceTrainer:
         over ``model.parameters()`` and keep that optimizer's state pointing at the trainer's buffers,
         so ``optimizer.state_dict()`` stays meaningful after training (single-GPU / allreduce modes)."""
         group = optimizer.param_groups[0]
-        t = cls(model, sampling, lr=group["lr"], betas=tuple(group["betas"]), eps=group["eps"], alpha=alpha,
+        t = cls(model, sampling, lr=float(group["lr"]), betas=tuple(group["betas"]), eps=group["eps"], alpha=alpha,
                 max_batch=max_batch, **kw)
+        # a stock torch.optim.Adam (the optimizer of the reference's quick-start, README.md:123-126) keeps its
+        # step count as a float32 CPU tensor; optim.DenseAdam as an int
+        t._step_as_tensor = type(optimizer) is torch.optim.Adam
         if t.mode not in ("colpar", "rowshard"):
             for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
                 st = optimizer.state[p]
@@ -80,15 +83,17 @@ class DeviceTrainer:
                     m.copy_(st["exp_avg"])
                     v.copy_(st["exp_avg_sq"])
                     t.t = max(t.t, int(st["step"]))
-                st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, t.t
+                st["exp_avg"], st["exp_avg_sq"] = m, v
             t._optimizer = optimizer
+            t.sync_optimizer_state()
         return t
 
     def sync_optimizer_state(self):
         opt = getattr(self, "_optimizer", None)
         if opt is not None:
             for p in (self.model.entity_embedding, self.model.relation_embedding):
-                opt.state[p]["step"] = self.t
+                opt.state[p]["step"] = (torch.tensor(float(self.t), dtype=torch.float32)
+                                        if getattr(self, "_step_as_tensor", False) else self.t)
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,

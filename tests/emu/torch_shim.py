@@ -38,7 +38,9 @@ def install():
 
     from . import build_emu
 
-    lib = C.CDLL(build_emu.build())
+    import os
+
+    lib = C.CDLL(os.environ.get("KGE_EMU_LIB") or build_emu.build())  # KGE_EMU_LIB: e.g. the sanitizer build
     for name, (res, args) in _native.PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

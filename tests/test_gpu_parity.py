@@ -415,15 +415,25 @@ def _toy_pipeline(route, pool, epochs=2):
     params = [p for p in m.parameters() if p.requires_grad]
     opt = optim.DenseAdam(params, lr=0.01) if route == "device" else torch.optim.Adam(params, lr=0.01)
     ev = evaluation.Evaluation(entities=ents, relations=rels, batch_size=8, true_triples=ds.true_triples, device=DEV)
-    pipe = compose.Pipeline(epochs=epochs, eval_every=1, device=DEV, fused=(route != "generic"))
+    # "adopted": the reference's own quick-start objects (a stock torch.optim.Adam) taken over by the device step
+    pipe = compose.Pipeline(epochs=epochs, eval_every=1, device=DEV, fused=(route != "generic"),
+                            adopt_torch_adam=(route == "adopted"))
     pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5), evaluation=ev)
+    if route == "adopted":
+        assert getattr(pipe, "_trainer", None) is not None, "torch.optim.Adam was not adopted"
+        st = opt.state[m.entity_embedding]
+        assert torch.is_tensor(st["step"]) and int(st["step"]) == pipe._trainer.t == epochs * 2 * -(-700 // 64)
+        assert st["exp_avg"].data_ptr() == pipe._trainer.m_ent.data_ptr() and st["exp_avg"].abs().sum().item() > 0
+        assert m.modulus.grad is None  # RotatE's unused trainable scalar stays untouched (rotate.py:66-67)
+    elif route != "device":
+        assert getattr(pipe, "_trainer", None) is None
     return m, pipe
 
 
 @pytest.mark.parametrize("pool", ("independent", "reference"))
 def test_pipeline_routes_agree(pool, capsys):
     ref, p0 = _toy_pipeline("generic", pool)
-    for route in ("fused", "device"):
+    for route in ("fused", "device", "adopted"):
         m, p = _toy_pipeline(route, pool)
         torch.testing.assert_close(m.entity_embedding, ref.entity_embedding, rtol=2e-3, atol=2e-4)
         torch.testing.assert_close(m.relation_embedding, ref.relation_embedding, rtol=2e-3, atol=2e-4)
