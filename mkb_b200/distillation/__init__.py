@@ -1,9 +1,12 @@
-"""The consumers of the score / top-k kernels in mkb's distillation add-on.
-
-Only the sampler that IS a "score every candidate -> keep the k best" reduce lives here
-(``TopKSampling``, mkb/distillation/top_k_sampling.py:321-677); the distillation training loop
-(``Distillation``, ``KdmkbModel``) and the faiss-based samplers are outside the hot path.
+"""mkb's distillation add-on on this package's kernels: the loss of a distillation
+step (``Distillation.distill``: 3-D samples through the score kernel, KL-divergence kernels) and the two
+samplers that need no nearest-neighbour index (``UniformSampling``; ``TopKSampling``, a "score every candidate
+-> keep the k best" reduce on the score + exact top-k kernels).  Mirrors mkb/distillation/{distillation,
+uniform_sampling,top_k_sampling}.py; the faiss-based samplers and the multi-KB ``KdmkbModel`` driver are not
+part of the hot path.
 """
+from .distillation import Distillation
 from .top_k_sampling import TopKSampling
+from .uniform_sampling import UniformSampling
 
-__all__ = ["TopKSampling"]
+__all__ = ["Distillation", "TopKSampling", "UniformSampling"]

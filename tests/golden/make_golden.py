@@ -507,6 +507,39 @@ def gen_distill_rows():
                 for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
                     out[f"{name}/{tag}/{call}/{k}"] = _np(t)
             assert teacher.training
+    # Distillation.distill (distillation/distillation.py:440-677): loss value + the student's autograd gradients
+    # for a supervised (UniformSampling) and an unsupervised (TopKSampling) sampler, teacher / student KGs that
+    # share only part of their labels (so some positives take part in one, two or none of the three terms)
+    sample2 = torch.tensor(np.stack([rng.randint(Nt, size=12), rng.randint(Rt, size=12), rng.randint(Nt, size=12)], 1))
+    out["sample2"] = _np(sample2)
+    for name in ("RotatE", "TransE", "ComplEx"):
+        torch.manual_seed(3)
+        teacher = getattr(models, name)(hidden_dim=D, entities=ent_t, relations=rel_t, gamma=6)
+        with torch.no_grad():
+            teacher.entity_embedding.mul_(3.0)
+        torch.manual_seed(5)
+        student = getattr(models, name)(hidden_dim=D, entities=ent_s, relations=rel_s, gamma=6)
+        with torch.no_grad():
+            student.entity_embedding.mul_(3.0)
+        out[f"{name}/s_ent"], out[f"{name}/s_rel"] = _np(student.entity_embedding), _np(student.relation_embedding)
+        for kind in ("uniform", "topk"):
+            if kind == "uniform":
+                smp = distillation.UniformSampling(batch_size_entity=5, batch_size_relation=3, seed=42)
+            else:
+                smp = distillation.TopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                                student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
+                                                n_random_entities=2, n_random_relations=1, seed=42)
+            proc = distillation.Distillation(teacher_entities=ent_t, student_entities=ent_s, teacher_relations=rel_t,
+                                             student_relations=rel_s, sampling=smp)
+            av = [proc.available(*map(int, row)) for row in sample2]
+            out[f"{name}/{kind}/avail"] = np.array([[a["head"], a["relation"], a["tail"]] for a in av])
+            for call in range(2):
+                student.zero_grad()
+                loss = proc.distill(teacher=teacher, student=student, sample=sample2)
+                loss.backward()
+                out[f"{name}/{kind}/{call}/loss"] = _np(loss)
+                out[f"{name}/{kind}/{call}/g_ent"] = _np(student.entity_embedding.grad)
+                out[f"{name}/{kind}/{call}/g_rel"] = _np(student.relation_embedding.grad)
     np.savez_compressed(os.path.join(HERE, "distill_rows.npz"), **out)
     print("distill_rows", len(out))
 

@@ -288,3 +288,44 @@ def test_top_k_sampling_matches_reference(model):
             for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), got):
                 np.testing.assert_array_equal(t.cpu().numpy(), d[f"{model}/{tag}/{call}/{k}"], err_msg=f"{tag}/{call}/{k}")
         assert teacher.training
+
+
+@pytest.mark.parametrize("model", ("RotatE", "TransE", "ComplEx"))
+@pytest.mark.parametrize("kind", ("uniform", "topk"))
+def test_distillation_loss_and_student_gradients_match_reference(model, kind):
+    """Distillation.distill (distillation/distillation.py:440-677): 3-D samples through the score kernel, three
+    KL divergences; loss and the student's gradients against the reference's autograd, two consecutive calls
+    (the samplers' RNG streams continue)."""
+    from mkb_b200 import distillation
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = getattr(models, model)(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6)
+    teacher._set_params(torch.from_numpy(d[f"{model}/ent"].copy()), torch.from_numpy(d[f"{model}/rel"].copy()))
+    student = getattr(models, model)(hidden_dim=8, entities=ent_s, relations=rel_s, gamma=6)
+    student._set_params(torch.from_numpy(d[f"{model}/s_ent"].copy()), torch.from_numpy(d[f"{model}/s_rel"].copy()))
+    teacher, student = teacher.to(DEV), student.to(DEV)
+    if kind == "uniform":
+        smp = distillation.UniformSampling(batch_size_entity=5, batch_size_relation=3, seed=42)
+    else:
+        smp = distillation.TopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                        student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
+                                        n_random_entities=2, n_random_relations=1, seed=42)
+    proc = distillation.Distillation(teacher_entities=ent_t, student_entities=ent_s, teacher_relations=rel_t,
+                                     student_relations=rel_s, sampling=smp, device=DEV)
+    sample = torch.from_numpy(d["sample2"])
+    av = [proc.available(*map(int, row)) for row in sample]
+    np.testing.assert_array_equal(np.array([[a["head"], a["relation"], a["tail"]] for a in av]), d[f"{model}/{kind}/avail"])
+    for call in range(2):
+        student.zero_grad()
+        loss = proc.distill(teacher=teacher, student=student, sample=sample)
+        loss.backward()
+        ref = float(d[f"{model}/{kind}/{call}/loss"])
+        assert abs(loss.item() - ref) <= 1e-4 * abs(ref), (call, loss.item(), ref)
+        for got, key in ((student.entity_embedding.grad, "g_ent"), (student.relation_embedding.grad, "g_rel")):
+            want = d[f"{model}/{kind}/{call}/{key}"]
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max(), (call, key)
+        assert teacher.entity_embedding.grad is None
