@@ -95,6 +95,20 @@ class BaseModel(nn.Module):
             return sample.reshape(sample.size(0) * sample.size(1), 3), (sample.size(0), sample.size(1))
         raise ValueError("sample must be 2-D [B,3] or 3-D [n,b,3]")
 
+    def batch(self, sample, negative_sample=None, mode=None):
+        """``(head, relation, tail, shape)`` embedding rows of a sample, shaped ``[B,1,dim]`` / ``[B,K,dim]`` as
+        mkb/models/base.py:153-207 returns them.  An accessor for callers that want the rows themselves
+        (``TransE._top_k``, nearest-neighbour samplers): ``forward`` never materialises these tensors — the
+        gathers happen inside the scoring kernels."""
+        flat, shape = self.format_sample(sample, negative_sample)
+        ent, rel = self.entity_embedding, self.relation_embedding
+        head, relation, tail = ent[flat[:, 0]].unsqueeze(1), rel[flat[:, 1]].unsqueeze(1), ent[flat[:, 2]].unsqueeze(1)
+        if mode == "head-batch":
+            head = ent[negative_sample.reshape(-1)].view(negative_sample.size(0), negative_sample.size(1), -1)
+        elif mode == "tail-batch":
+            tail = ent[negative_sample.reshape(-1)].view(negative_sample.size(0), negative_sample.size(1), -1)
+        return head, relation, tail, shape
+
     # -- kernels ---------------------------------------------------------------------------
     @property
     def spec(self):

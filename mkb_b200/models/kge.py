@@ -12,6 +12,12 @@ __all__ = ["TransE", "DistMult", "ComplEx", "RotatE", "pRotatE"]
 class TransE(BaseModel):
     """score = gamma - || h + r - t ||_1   (mkb/models/transe.py:55-76)."""
 
+    def _top_k(self, sample):
+        """The points whose nearest entity / relation rows are the best heads, relations and tails of each
+        triple: ``t - r``, ``t - h``, ``h + r`` (transe.py:78-84)."""
+        head, relation, tail, _ = self.batch(sample=sample)
+        return tail - relation, tail - head, head + relation
+
 
 class DistMult(BaseModel):
     """score = sum_d h * r * t   (mkb/models/distmult.py:53-75)."""

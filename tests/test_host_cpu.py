@@ -384,3 +384,30 @@ def test_top_k_sampling_host_logic_matches_reference(name, monkeypatch):
             for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), got):
                 np.testing.assert_array_equal(t.numpy(), d[f"{name}/{tag}/{call}/{k}"], err_msg=f"{tag}/{call}/{k}")
         assert teacher.training
+
+
+def test_batch_accessor_and_transe_top_k():
+    """BaseModel.batch / TransE._top_k (mkb/models/base.py:153-207, transe.py:78-84): pure row indexing, usable
+    without CUDA; shapes and values as the reference returns them."""
+    ents, rels = {f"e{i}": i for i in range(9)}, {f"r{i}": i for i in range(3)}
+    m = models.ComplEx(hidden_dim=4, entities=ents, relations=rels, gamma=6)
+    E, R = m.entity_embedding.detach().numpy(), m.relation_embedding.detach().numpy()
+    s, n = torch.tensor([[0, 1, 2], [3, 0, 4]]), torch.tensor([[1, 2, 3], [5, 6, 7]])
+    h, r, t, shape = m.batch(s)
+    assert tuple(shape) == (2, 1) and h.shape == (2, 1, 8) and r.shape == (2, 1, 8)
+    np.testing.assert_array_equal(h[:, 0].detach().numpy(), E[[0, 3]])
+    np.testing.assert_array_equal(r[:, 0].detach().numpy(), R[[1, 0]])
+    h, r, t, shape = m.batch(s, n, "head-batch")
+    assert tuple(shape) == (2, 3) and h.shape == (2, 3, 8) and t.shape == (2, 1, 8)
+    np.testing.assert_array_equal(h.detach().numpy(), E[n.numpy()])
+    h, r, t, shape = m.batch(s, n, "tail-batch")
+    np.testing.assert_array_equal(t.detach().numpy(), E[n.numpy()])
+    np.testing.assert_array_equal(h[:, 0].detach().numpy(), E[[0, 3]])
+    h, r, t, shape = m.batch(torch.stack([s, s, s]))
+    assert tuple(shape) == (3, 2) and h.shape == (6, 1, 8)
+    te = models.TransE(hidden_dim=4, entities=ents, relations=rels, gamma=6)
+    eh, er, et = te._top_k(s)
+    E, R = te.entity_embedding.detach().numpy(), te.relation_embedding.detach().numpy()
+    np.testing.assert_allclose(eh[:, 0].detach().numpy(), E[[2, 4]] - R[[1, 0]])
+    np.testing.assert_allclose(er[:, 0].detach().numpy(), E[[2, 4]] - E[[0, 3]])
+    np.testing.assert_allclose(et[:, 0].detach().numpy(), E[[0, 3]] + R[[1, 0]])
