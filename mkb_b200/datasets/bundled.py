@@ -10,11 +10,11 @@ constructor arguments.
 """
 from __future__ import annotations
 
-import csv
 import importlib.util
 import json
 import os
 
+from ..utils.io import read_csv_classification
 from .dataset import Dataset, _read_csv
 
 __all__ = ["Wn18rr", "Fb15k237", "Yago310"]
@@ -44,21 +44,7 @@ def _locate(name, path=None):
 
 
 def _read_classification(path):
-    """``h,r,t,label`` rows -> {"X": [[h,r,t]], "y": [label]} (mkb/utils/read_csv.py read_csv_classification)."""
-    if not os.path.exists(path):
-        return None
-    X, y = [], []
-    with open(path) as f:
-        for row in csv.reader(f):
-            if len(row) < 4:
-                continue
-            try:
-                h, r, t, lab = (int(v) for v in row[:4])
-            except ValueError:  # header
-                continue
-            X.append([h, r, t])
-            y.append(lab)
-    return {"X": X, "y": y}
+    return read_csv_classification(path) if os.path.exists(path) else None
 
 
 class _Bundled(Dataset):

@@ -1,7 +1,7 @@
 """tqdm wrapper with the reference's interface (mkb/utils/bar.py:6-35)."""
 import tqdm
 
-__all__ = ["Bar"]
+__all__ = ["Bar", "BarRange"]
 
 
 class Bar:
@@ -18,3 +18,10 @@ class Bar:
         for x in self.bar:
             self.n += 1
             yield x
+
+
+class BarRange(Bar):
+    """``BarRange(step, update_every, position=0)``: the same bar over ``range(step)`` (mkb/utils/bar.py:38-69)."""
+
+    def __init__(self, step, update_every=1, position=0):
+        super().__init__(range(step), update_every=update_every, position=position)
