@@ -1,12 +1,12 @@
 """mkb's distillation add-on on this package's kernels: the loss of a distillation
 step (``Distillation.distill``: 3-D samples through the score kernel, KL-divergence kernels) and the two
-samplers that need no nearest-neighbour index (``UniformSampling``; ``TopKSampling``, a "score every candidate
+samplers that need no nearest-neighbour index (``UniformSampling``; ``TopKSampling`` and its pre-computed form ``FastTopKSampling``, a "score every candidate
 -> keep the k best" reduce on the score + exact top-k kernels).  Mirrors mkb/distillation/{distillation,
-uniform_sampling,top_k_sampling}.py; the faiss-based samplers and the multi-KB ``KdmkbModel`` driver are not
+uniform_sampling,top_k_sampling}.py; the faiss-based sampler (``TopKSamplingTransE``) and the multi-KB ``KdmkbModel`` driver are not
 part of the hot path.
 """
 from .distillation import Distillation
-from .top_k_sampling import TopKSampling
+from .top_k_sampling import FastTopKSampling, TopKSampling
 from .uniform_sampling import UniformSampling
 
-__all__ = ["Distillation", "TopKSampling", "UniformSampling"]
+__all__ = ["Distillation", "FastTopKSampling", "TopKSampling", "UniformSampling"]

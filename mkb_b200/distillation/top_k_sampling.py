@@ -19,7 +19,7 @@ import torch
 
 from .. import ops
 
-__all__ = ["TopKSampling"]
+__all__ = ["FastTopKSampling", "TopKSampling"]
 
 
 class TopKSampling:
@@ -98,6 +98,93 @@ class TopKSampling:
         # the reference indexes relations_student for BOTH relation outputs (:604-607); kept
         relation_teacher, relation_student = rel_s[rank_r], rel_s[rank_r]
 
+        if self.n_random_entities > 0:  # _randomize_distribution :894-925, same RNG consumption
+            rnd_t = self._rng.choice(list(self.mapping_entities.keys()), size=self.n_random_entities, replace=False)
+            rnd_s = torch.tensor([[self.mapping_entities[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            head_teacher, head_student = torch.cat([head_teacher, rnd_t], 1), torch.cat([head_student, rnd_s], 1)
+            tail_teacher, tail_student = torch.cat([tail_teacher, rnd_t], 1), torch.cat([tail_student, rnd_s], 1)
+        if self.n_random_relations > 0:  # :927-949
+            rnd_t = self._rng.choice(list(self.mapping_relations.keys()), size=self.n_random_relations, replace=False)
+            rnd_s = torch.tensor([[self.mapping_relations[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            relation_teacher = torch.cat([relation_teacher, rnd_t], 1)
+            relation_student = torch.cat([relation_student, rnd_s], 1)
+        return (head_teacher, relation_teacher, tail_teacher, head_student, relation_student, tail_student)
+
+
+class FastTopKSampling:
+    """``TopKSampling`` evaluated ONCE for every training triple of the teacher's dataset, then looked up
+    (mkb/distillation/top_k_sampling.py:10-318).  The reference fills six Python dicts keyed by the strings
+    ``"r_t"`` / ``"h_t"`` / ``"h_r"`` in a loop over every triple of every head-batch; here the pre-computation
+    is the batched kernel path of ``TopKSampling.get`` and the tables are three sorted int64 key vectors with
+    their ``[n_keys, k]`` rows on the teacher's device, so ``get`` is three ``searchsorted`` calls.
+
+    A TransE teacher makes the reference switch to its faiss nearest-neighbour sampler
+    (``TopKSamplingTransE``, :168-171), which this package does not provide: that case raises."""
+
+    def __init__(self, teacher_entities, teacher_relations, student_entities, student_relations, batch_size_entity,
+                 batch_size_relation, n_random_entities, n_random_relations, dataset_teacher, teacher, device="cpu",
+                 seed=None, **kwargs):
+        if teacher.name == "TransE":
+            raise NotImplementedError("FastTopKSampling with a TransE teacher uses the reference's faiss sampler "
+                                      "(TopKSamplingTransE), which is outside this package")
+        base = TopKSampling(teacher_entities=teacher_entities, teacher_relations=teacher_relations,
+                            student_entities=student_entities, student_relations=student_relations,
+                            batch_size_entity=batch_size_entity, batch_size_relation=batch_size_relation,
+                            n_random_entities=0, n_random_relations=0, device=device, seed=seed)
+        self.mapping_entities, self.mapping_relations = base.mapping_entities, base.mapping_relations
+        self.batch_size_entity_top_k = batch_size_entity
+        self.batch_size_relation_top_k = batch_size_relation
+        self.n_random_entities = n_random_entities
+        self.n_random_relations = n_random_relations
+        self._rng = np.random.RandomState(seed)
+        self.device = device
+        dev = teacher.entity_embedding.device
+        self._span = int(max(teacher.n_entity, teacher.n_relation)) + 1
+        samples = [data["sample"] for data in dataset_teacher if data["mode"] == "head-batch"]  # :218-220
+        samples = torch.cat(samples).to(dev) if samples else torch.zeros((0, 3), dtype=torch.int64, device=dev)
+        out = base.get(samples, teacher)
+        h, r, t = samples[:, 0], samples[:, 1], samples[:, 2]
+        # the head candidates of a triple depend on (r, t) only, the relations on (h, t), the tails on (h, r):
+        # one row per distinct key (the reference's dict keeps the last occurrence; all occurrences are equal)
+        self._tables = {}
+        for name, key, teacher_rows, student_rows in (("head", r * self._span + t, out[0], out[3]),
+                                                      ("relation", h * self._span + t, out[1], out[4]),
+                                                      ("tail", h * self._span + r, out[2], out[5])):
+            keys, inverse = torch.unique(key, return_inverse=True)
+            first = torch.full((keys.shape[0],), key.shape[0], dtype=torch.int64, device=dev)
+            first.scatter_reduce_(0, inverse, torch.arange(key.shape[0], device=dev), reduce="amin")
+            self._tables[name] = (keys, teacher_rows[first], student_rows[first])
+
+    @property
+    def supervised(self):
+        return False
+
+    @property
+    def batch_size_entity(self):
+        return self.batch_size_entity_top_k + self.n_random_entities
+
+    @property
+    def batch_size_relation(self):
+        return self.batch_size_relation_top_k + self.n_random_relations
+
+    def _lookup(self, name, key):
+        keys, teacher_rows, student_rows = self._tables[name]
+        pos = torch.searchsorted(keys, key).clamp_(max=max(keys.shape[0] - 1, 0))
+        if keys.shape[0] == 0 or not bool((keys[pos] == key).all()):
+            bad = key[(keys[pos] != key)][0].item() if keys.shape[0] else key[0].item()
+            raise KeyError(f"{bad // self._span}_{bad % self._span}")  # the reference's dict lookup fails the same way
+        return teacher_rows[pos], student_rows[pos]
+
+    def get(self, sample, **kwargs):
+        dev = self._tables["head"][0].device
+        sample = sample.to(dev)
+        B = sample.shape[0]
+        h, r, t = sample[:, 0], sample[:, 1], sample[:, 2]
+        head_teacher, head_student = self._lookup("head", r * self._span + t)
+        relation_teacher, relation_student = self._lookup("relation", h * self._span + t)
+        tail_teacher, tail_student = self._lookup("tail", h * self._span + r)
         if self.n_random_entities > 0:  # _randomize_distribution :894-925, same RNG consumption
             rnd_t = self._rng.choice(list(self.mapping_entities.keys()), size=self.n_random_entities, replace=False)
             rnd_s = torch.tensor([[self.mapping_entities[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)

@@ -540,6 +540,25 @@ def gen_distill_rows():
                 out[f"{name}/{kind}/{call}/loss"] = _np(loss)
                 out[f"{name}/{kind}/{call}/g_ent"] = _np(student.entity_embedding.grad)
                 out[f"{name}/{kind}/{call}/g_rel"] = _np(student.relation_embedding.grad)
+    # FastTopKSampling (:10-318): pre-computed over the teacher's training set, looked up per batch
+    train = sorted({(int(rng.randint(Nt)), int(rng.randint(Rt)), int(rng.randint(Nt))) for _ in range(40)})
+    out["fast/train"] = np.array(train)
+    for name in ("RotatE", "ComplEx"):
+        torch.manual_seed(3)
+        teacher = getattr(models, name)(hidden_dim=D, entities=ent_t, relations=rel_t, gamma=6)
+        with torch.no_grad():
+            teacher.entity_embedding.mul_(3.0)
+        ds = datasets.Dataset(train=train, entities=ent_t, relations=rel_t, batch_size=7, shuffle=False, seed=42)
+        smp = distillation.FastTopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                            student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
+                                            n_random_entities=2, n_random_relations=1, seed=42, teacher=teacher,
+                                            dataset_teacher=ds)
+        q = torch.tensor(train[3:29:5])
+        out["fast/query"] = _np(q)
+        for call in range(2):
+            res = smp.get(sample=q)
+            for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
+                out[f"fast/{name}/{call}/{k}"] = _np(t)
     np.savez_compressed(os.path.join(HERE, "distill_rows.npz"), **out)
     print("distill_rows", len(out))
 

@@ -329,3 +329,40 @@ def test_distillation_loss_and_student_gradients_match_reference(model, kind):
             want = d[f"{model}/{kind}/{call}/{key}"]
             assert np.abs(got.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max(), (call, key)
         assert teacher.entity_embedding.grad is None
+
+
+@pytest.mark.parametrize("model", ("RotatE", "ComplEx"))
+def test_fast_top_k_sampling_matches_reference(model):
+    """FastTopKSampling (top_k_sampling.py:10-318): pre-computed over the teacher's training set with the batched
+    kernel path, looked up by searchsorted; same rows and the same RNG stream as the reference's dict tables."""
+    from mkb_b200 import datasets, distillation
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = getattr(models, model)(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6)
+    teacher._set_params(torch.from_numpy(d[f"{model}/ent"].copy()), torch.from_numpy(d[f"{model}/rel"].copy()))
+    teacher = teacher.to(DEV)
+    train = [tuple(int(x) for x in row) for row in d["fast/train"]]
+    ds = datasets.Dataset(train=train, entities=ent_t, relations=rel_t, batch_size=7, shuffle=False, seed=42)
+    smp = distillation.FastTopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                        student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
+                                        n_random_entities=2, n_random_relations=1, seed=42, teacher=teacher,
+                                        dataset_teacher=ds)
+    assert (smp.batch_size_entity, smp.batch_size_relation, smp.supervised) == (6, 3, False)
+    q = torch.from_numpy(d["fast/query"])
+    for call in range(2):
+        got = smp.get(sample=q)
+        for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), got):
+            np.testing.assert_array_equal(t.cpu().numpy(), d[f"fast/{model}/{call}/{k}"], err_msg=f"{call}/{k}")
+    with pytest.raises(KeyError):  # a triple whose (r, t) never occurred in the teacher's training set
+        unseen = next((h, r, t) for h in range(60) for r in range(7) for t in range(60)
+                      if not any(r == b and t == c for _, b, c in train))
+        smp.get(sample=torch.tensor([unseen]))
+    with pytest.raises(NotImplementedError):
+        te = models.TransE(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6).to(DEV)
+        distillation.FastTopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                      student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
+                                      n_random_entities=0, n_random_relations=0, teacher=te, dataset_teacher=ds)
