@@ -411,3 +411,21 @@ def test_batch_accessor_and_transe_top_k():
     np.testing.assert_allclose(eh[:, 0].detach().numpy(), E[[2, 4]] - R[[1, 0]])
     np.testing.assert_allclose(er[:, 0].detach().numpy(), E[[2, 4]] - E[[0, 3]])
     np.testing.assert_allclose(et[:, 0].detach().numpy(), E[[0, 3]] + R[[1, 0]])
+
+
+def test_pipeline_recognises_only_a_stock_torch_adam():
+    """Only the optimizer of the reference's quick-start (README.md:123-126) is taken over by the device step."""
+    from mkb_b200 import compose
+
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    ok = compose.Pipeline._plain_torch_adam
+    assert ok(torch.optim.Adam(p, lr=5e-5))
+    assert not ok(torch.optim.Adam(p, lr=5e-5, weight_decay=1e-3))
+    assert not ok(torch.optim.Adam(p, lr=5e-5, amsgrad=True))
+    assert not ok(torch.optim.Adam(p, lr=torch.tensor(5e-5)))
+    assert not ok(torch.optim.AdamW(p, lr=5e-5))
+    assert not ok(torch.optim.SGD(p, lr=0.1))
+    assert not ok(torch.optim.Adam([{"params": p}, {"params": [torch.nn.Parameter(torch.zeros(2))]}], lr=1e-3))
+    # CPU model: never adopted, the generic route raises from the kernels ("CUDA only"), not from the trainer
+    pipe = compose.Pipeline(epochs=1)
+    assert pipe.adopt_torch_adam and compose.Pipeline(epochs=1, adopt_torch_adam=False).adopt_torch_adam is False
