@@ -53,3 +53,22 @@ for rows, cols, k in ((1, N, 10), (64, N, 100), (1024, N, 64)):
         b.record()
         torch.cuda.synchronize()
         print(f"top-{k} of {rows} x {cols}: {name} {a.elapsed_time(b) / 10 * 1e3:.0f} us", flush=True)
+
+# distillation.TopKSampling.get: the reference loops over the batch with three model calls + three full argsorts per
+# triple (mkb/distillation/top_k_sampling.py:577-604); here the whole batch is scored and reduced per chunk
+from mkb_b200 import distillation
+
+ents, rels = {i: i for i in range(N)}, {i: i for i in range(R)}
+torch.manual_seed(0)
+teacher = models.RotatE(hidden_dim=D, entities=ents, relations=rels, gamma=6.0).to(dev)
+smp = distillation.TopKSampling(teacher_entities=ents, teacher_relations=rels, student_entities=ents,
+                                student_relations=rels, batch_size_entity=100, batch_size_relation=5,
+                                n_random_entities=10, n_random_relations=2, seed=42)
+batch = torch.from_numpy(test[:256]).to(dev)
+smp.get(batch[:8], teacher)
+torch.cuda.synchronize()
+t0 = time.time()
+out = smp.get(batch, teacher)
+torch.cuda.synchronize()
+print(f"TopKSampling.get: {1e3 * (time.time() - t0):.1f} ms for {batch.shape[0]} triples x {N} candidate entities "
+      f"(2 modes) + {R} relations, k = 100 / 5 -> {tuple(out[0].shape)}, {tuple(out[1].shape)}", flush=True)

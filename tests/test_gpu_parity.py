@@ -14,7 +14,7 @@ if torch.cuda.is_available():
     import mkb_b200
     from mkb_b200 import evaluation, losses, models, ops, optim, sampling
 
-from conftest import DEV  # "cuda" (or "cpu" under the KGE_TEST_EMU developer shim)
+from conftest import DEV, EMU  # "cuda" (or "cpu" under the KGE_TEST_EMU developer shim)
 
 
 def _model(name, ent, rel, gamma):
@@ -391,6 +391,7 @@ def test_dense_adam_matches_torch():
     torch.testing.assert_close(p2, p1, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.skipif(EMU, reason="the developer shim disables exactly this check")
 def test_cpu_tensors_fail_loudly():
     m = models.TransE(hidden_dim=4, entities={0: 0, 1: 1}, relations={0: 0}, gamma=3)
     with pytest.raises(RuntimeError, match="CUDA only"):
