@@ -10,6 +10,7 @@ installed, so a throw-away shim (Mean / RollingMean) is written to a temp dir an
 running it (scores, losses, autograd gradients, sampler draws, filter lists, ranks) are
 stored as small ``.npz`` files next to this script.
 """
+import collections
 import os
 import sys
 import tempfile
@@ -559,6 +560,34 @@ def gen_distill_rows():
             res = smp.get(sample=q)
             for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
                 out[f"fast/{name}/{call}/{k}"] = _np(t)
+    # KdmkbModel.forward (kdmkb_model.py:286-360): two KBs with partly shared labels trained together for a few
+    # steps; per-step losses of both models and the final tables
+    train_s = sorted({(int(rng.randint(Ns)), int(rng.randint(Rs)), int(rng.randint(Ns))) for _ in range(36)})
+    out["kd/train_s"] = np.array(train_s)
+    kd_models = {"a": ("RotatE", ent_t, rel_t, train, 3), "b": ("ComplEx", ent_s, rel_s, train_s, 5)}
+    ms, dss = collections.OrderedDict(), collections.OrderedDict()
+    for key, (name, ents_, rels_, tr, sd) in kd_models.items():
+        torch.manual_seed(sd)
+        ms[key] = getattr(models, name)(hidden_dim=D, entities=ents_, relations=rels_, gamma=6)
+        with torch.no_grad():
+            ms[key].entity_embedding.mul_(3.0)
+        # copies: _np() aliases the parameter's storage, which the optimizer then updates in place
+        out[f"kd/{key}/ent0"] = _np(ms[key].entity_embedding).copy()
+        out[f"kd/{key}/rel0"] = _np(ms[key].relation_embedding).copy()
+        dss[key] = datasets.Dataset(train=tr, valid=tr[:6], test=tr[6:12], entities=ents_, relations=rels_, batch_size=6,
+                                    shuffle=False, seed=42)
+    per = lambda v: {"a": v, "b": v}
+    kd = distillation.KdmkbModel(models=ms, datasets=dss, lr=per(0.01), alpha_kl=per(0.4), alpha_adv=per(0.5),
+                                 negative_sampling_size=per(5), batch_size_entity=per(4), batch_size_relation=per(2),
+                                 n_random_entities=per(2), n_random_relations=per(1), update_distillation_every=1000,
+                                 device="cpu", seed=42, warm_step=0)
+    losses_ = []
+    for step in range(4):
+        m = kd.forward(dss, ms, weight_kl={"a": 0.4, "b": 0.4})
+        losses_.append([m["a"].get(), m["b"].get()])
+    out["kd/rolling_loss"] = np.array(losses_)
+    for key in ms:
+        out[f"kd/{key}/ent1"], out[f"kd/{key}/rel1"] = _np(ms[key].entity_embedding), _np(ms[key].relation_embedding)
     np.savez_compressed(os.path.join(HERE, "distill_rows.npz"), **out)
     print("distill_rows", len(out))
 

@@ -366,3 +366,46 @@ def test_fast_top_k_sampling_matches_reference(model):
         distillation.FastTopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
                                       student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
                                       n_random_entities=0, n_random_relations=0, teacher=te, dataset_teacher=ds)
+
+
+def test_kdmkb_model_steps_track_reference():
+    """KdmkbModel.forward (kdmkb_model.py:286-360): two KBs with partly shared labels, each distilling from the
+    other; the rolling losses of both models over four steps and the trained tables against the reference run
+    (same shared-pool negatives, same FastTopKSampling RNG streams, torch.optim.Adam)."""
+    import collections
+
+    from mkb_b200 import datasets, distillation
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    spec = {"a": ("RotatE", ent_t, rel_t, d["fast/train"]), "b": ("ComplEx", ent_s, rel_s, d["kd/train_s"])}
+    ms, dss = collections.OrderedDict(), collections.OrderedDict()
+    for key, (name, ents_, rels_, tr) in spec.items():
+        tr = [tuple(int(x) for x in row) for row in tr]
+        m = getattr(models, name)(hidden_dim=8, entities=ents_, relations=rels_, gamma=6)
+        m._set_params(torch.from_numpy(d[f"kd/{key}/ent0"].copy()), torch.from_numpy(d[f"kd/{key}/rel0"].copy()))
+        ms[key] = m.to(DEV)
+        dss[key] = datasets.Dataset(train=tr, valid=tr[:6], test=tr[6:12], entities=ents_, relations=rels_, batch_size=6,
+                                    shuffle=False, seed=42)
+
+    def per(v):
+        return {"a": v, "b": v}
+
+    kd = distillation.KdmkbModel(models=ms, datasets=dss, lr=per(0.01), alpha_kl=per(0.4), alpha_adv=per(0.5),
+                                 negative_sampling_size=per(5), batch_size_entity=per(4), batch_size_relation=per(2),
+                                 n_random_entities=per(2), n_random_relations=per(1), update_distillation_every=1000,
+                                 device=DEV, seed=42, warm_step=0, pool="reference")
+    got = []
+    for _ in range(4):
+        m = kd.forward(dss, ms, weight_kl={"a": 0.4, "b": 0.4})
+        got.append([m["a"].get(), m["b"].get()])
+    np.testing.assert_allclose(np.array(got), d["kd/rolling_loss"], rtol=2e-4)
+    for key in ms:  # Adam turns a near-zero gradient into a full +-lr step: compare as a fraction, like the trainers
+        for name, init, ref in (("entity_embedding", "ent0", "ent1"), ("relation_embedding", "rel0", "rel1")):
+            upd_ref = d[f"kd/{key}/{ref}"] - d[f"kd/{key}/{init}"]
+            upd = getattr(ms[key], name).detach().cpu().numpy() - d[f"kd/{key}/{init}"]
+            assert np.abs(upd_ref).max() > 0
+            assert (np.abs(upd - upd_ref) > 0.05 * np.abs(upd_ref).max()).mean() < 0.01, (key, name)
