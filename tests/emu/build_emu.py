@@ -4,7 +4,7 @@ for the HOST against the CUDA execution-model emulation in tests/emu/include/cud
 The product sources are not modified: this script rewrites, on the fly, the three constructs g++
 cannot parse
 
-  * ``kernel<<<grid, block, smem, stream>>>(args)``  ->  ``emu::launch(grid, block, smem, stream, [&]{ kernel(args); })``
+  * ``kernel<<<grid, block, smem, stream>>>(args)``  ->  ``emu::launch(&kernel, grid, block, smem, stream, [&]{ kernel(args); })``
   * ``extern __shared__ [__align__(n)] T name[];``   ->  ``T* name = (T*)emu::S.dyn_smem;``
   * the inline-PTX statements (red.*.add[.v4].f32, sqrt/rsqrt.approx) -> plain C++
 
@@ -90,8 +90,8 @@ def rewrite_launches(text):
         while len(parts) < 4:
             parts.append("0")
         out.append(text[pos:j])
-        out.append(f"emu::launch({parts[0]}, {parts[1]}, (size_t)({parts[2]}), (cudaStream_t)({parts[3]}), "
-                   f"[&]() {{ {kernel}({args}); }})")
+        out.append(f"emu::launch(emu::fn_addr({kernel}), {parts[0]}, {parts[1]}, (size_t)({parts[2]}), "
+                   f"(cudaStream_t)({parts[3]}), [&]() {{ {kernel}({args}); }})")
         pos = a1
 
 

@@ -88,8 +88,24 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   p->minor = 0;
   return cudaSuccess;
 }
+namespace emu {
+// kernels that opted in to more than 48 KB of dynamic shared memory (cudaFuncAttributeMaxDynamicSharedMemorySize)
+inline std::vector<std::pair<const void*, size_t>> smem_optin;
+template <class R, class... A>
+inline const void* fn_addr(R (*f)(A...)) {  // a kernel name or a variable holding a kernel pointer
+  return reinterpret_cast<const void*>(f);
+}
+inline size_t optin_of(const void* k) {
+  size_t best = 0;
+  for (auto& e : smem_optin)
+    if (e.first == k) best = e.second;
+  return best;
+}
+}  // namespace emu
 template <class F>
-inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
+inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute, int bytes) {
+  if (bytes > 232448) return 1;  // cudaErrorInvalidValue
+  emu::smem_optin.push_back({reinterpret_cast<const void*>(f), (size_t)bytes});
   return cudaSuccess;
 }
 inline const char* cudaGetErrorString(cudaError_t e) {
@@ -238,7 +254,12 @@ inline void run_block(int nthreads) {
 }
 
 template <class F>
-inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F&& body) {
+inline void launch(const void* kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, F&& body) {
+  if (smem > 48 * 1024 && optin_of(kernel) < smem) {  // a launch above 48 KB needs the opt-in attribute first
+    fprintf(stderr, "cuda_emu: %zu bytes of dynamic shared memory without cudaFuncSetAttribute opt-in\n", smem);
+    last_error = 1;
+    return;
+  }
   // the launch limits of sm_100 (cudaErrorInvalidConfiguration = 9 on the device; here too, and nothing runs)
   const unsigned long long nthreads_ll = (unsigned long long)block.x * block.y * block.z;
   if (grid.x == 0 || grid.y == 0 || grid.z == 0 || nthreads_ll == 0 || nthreads_ll > 1024 || block.x > 1024 ||

@@ -684,3 +684,52 @@ def test_sampler_status_word_on_exhausted_true_sets():
     assert status[0] & 4 and not out[0].any() and not pos[0].any()
     np.testing.assert_array_equal(out[1], [1, 0, 1, 1])  # survivors 1, 0, 1 repeat cyclically
     np.testing.assert_array_equal(pos[1], [1, 3, 6, 1])
+
+
+@pytest.mark.parametrize("model,K", [("RotatE", 13000), ("TransE", 40000)])
+def test_fused_forward_in_the_opt_in_shared_memory_window(model, K):
+    """K large enough that one CTA's dynamic shared memory (query + K scores) lies between 48 KB and the 200 KB
+    cap: the launch needs cudaFuncAttributeMaxDynamicSharedMemorySize first (the emulation refuses it otherwise,
+    like the device).  Beyond the cap the entry point reports KGE_E_UNSUPPORTED and callers take the unfused route."""
+    l = H.lib()
+    D, B, Nn, R, gamma = 8, 2, 50, 3, 6.0
+    ent, rel, sample, neg, w = _problem(model, Nn, R, D, B, K, seed=K)
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, "tail-batch")
+    loss, pos, ngs, _, _ = ko.train_step(model, ent, rel, sample, neg, "tail-batch", w, gamma=gamma)[:5]
+    _close(f["pos"], pos)
+    _close(f["neg"], ngs)
+    assert abs(f["stats"][3] - loss) <= 1e-5 * abs(loss)
+    # past the cap
+    K2 = 60000
+    neg2 = np.zeros((B, K2), np.int64)
+    tb = H.tables(model, ent, rel, gamma)
+    ws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, dtype=np.uint8)
+    out = [np.zeros((B, 1), np.float32), np.zeros((B, K2), np.float32), np.zeros(B, np.float32),
+           np.zeros((B, K2), np.float32), np.zeros(4, np.float32)]
+    assert l.kge_fused_fwd(C.byref(tb), 0, H.P(sample), B, H.P(neg2), K2, H.P(w), 0.5, *[H.P(o) for o in out], H.P(ws),
+                           None) == -6
+
+
+def test_pooled_adv_kernel_in_the_opt_in_shared_memory_window():
+    """pooled_adv_kernel keeps K scores + P dS entries in dynamic shared memory: (K + P) * 4 > 48 KB takes the
+    opt-in path; same scores / loss terms as the gather kernels on the negatives the positions select."""
+    l = H.lib()
+    model, mode, D, B, Nn, R, gamma = "DistMult", "head-batch", 4, 2, 40, 3, 6.0
+    K, Pn = 5000, 9000
+    rng = np.random.RandomState(3)
+    ent, rel, sample, _, w = _problem(model, Nn, R, D, B, 1, seed=17)
+    pool = rng.randint(Nn, size=Pn).astype(np.int64)
+    pos_idx = rng.randint(Pn, size=(B, K)).astype(np.int32)
+    neg = pool[pos_idx]
+    f = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    tb = H.tables(model, ent, rel, gamma)
+    ws = np.full(l.kge_pooled_workspace_bytes(C.byref(tb), B, K, Pn) + 64, 0xCD, np.uint8)
+    wsp = (ws.ctypes.data + 63) & ~63
+    lws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, np.uint8)
+    ps, ns = np.full((B, 1), np.nan, np.float32), np.full((B, K), np.nan, np.float32)
+    cpos, stats = np.full(B, np.nan, np.float32), np.zeros(4, np.float32)
+    H.ok(l.kge_pooled_dot_fwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(pool), Pn, H.P(pos_idx), K, H.P(w), 0.5,
+                              H.P(ps), H.P(ns), H.P(cpos), H.P(stats), wsp, H.P(lws), None), "kge_pooled_dot_fwd")
+    _close(ps, f["pos"].astype(np.float64), 1e-5)
+    _close(ns, f["neg"].astype(np.float64), 1e-5)
+    np.testing.assert_allclose(stats, f["stats"], rtol=1e-5)
