@@ -58,6 +58,7 @@ struct ByEntParams {
   float phase_div;
   float lr_bc1, inv_sqrt_bc2, b1, b2, eps;
 };
+static_assert(sizeof(ByEntParams) <= 4096, "kernel parameters are passed by value: 4 KB limit");
 
 template <int M, bool HEAD>
 __global__ void __launch_bounds__(kThreads) build_query_kernel(ByEntParams p) {

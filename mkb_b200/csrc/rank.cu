@@ -61,6 +61,7 @@ struct RankParams {
   const float* shard[KGE_MAX_SHARDS];
   unsigned n_shards;  // 0: unsharded
 };
+static_assert(sizeof(RankParams) <= 4096, "kernel parameters are passed by value: 4 KB limit");
 
 __device__ __forceinline__ const float* rk_entity_row(const RankParams& p, int64_t id) {
   if (p.n_shards == 0) return p.ent + id * (int64_t)p.ent_stride;

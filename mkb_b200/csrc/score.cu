@@ -56,6 +56,7 @@ struct FwdParams {
   const float* shard[KGE_MAX_SHARDS];
   unsigned n_shards;
 };
+static_assert(sizeof(FwdParams) <= 4096, "kernel parameters are passed by value: 4 KB limit");
 
 // Row of an entity from a split id (kge_common.cuh: shard_split): unsharded = id * stride.
 template <bool SHARD, typename P>
@@ -308,6 +309,7 @@ struct BwdParams {
   float* gr_buf;
   int shared_stats;  // multi-record launch whose `stats` is ONE already-global buffer (not one per record)
 };
+static_assert(sizeof(BwdParams) <= 4096, "kernel parameters are passed by value: 4 KB limit");
 
 // Gradient row of an entity from a split id: in the owner's (possibly remote) gradient shard.
 template <bool SHARD>

@@ -686,7 +686,7 @@ def test_sampler_status_word_on_exhausted_true_sets():
     np.testing.assert_array_equal(pos[1], [1, 3, 6, 1])
 
 
-@pytest.mark.parametrize("model,K", [("RotatE", 13000), ("TransE", 40000)])
+@pytest.mark.parametrize("model,K", [("RotatE", 13000), ("TransE", 20000)])
 def test_fused_forward_in_the_opt_in_shared_memory_window(model, K):
     """K large enough that one CTA's dynamic shared memory (query + K scores) lies between 48 KB and the 200 KB
     cap: the launch needs cudaFuncAttributeMaxDynamicSharedMemorySize first (the emulation refuses it otherwise,
