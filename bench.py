@@ -339,9 +339,10 @@ def run_ours(args):
     e2e_steps = 2 * half
     pipe = compose.Pipeline(epochs=1, device=dev, trainer_options=topts)
     sys.stderr, _err = open(os.devnull, "w"), sys.stderr  # tqdm's bar
+    e2e_error = None
+    e2e_passes = []
     try:
         pipe.learn(model=model2, dataset=ds_warm, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
-        e2e_passes = []
         for _ in range(2):  # two full passes; the faster one is reported (a cold first pass has been seen
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)  # to pay
             barrier()  # one-off driver/allocator costs), both are listed in e2e.passes_ms_per_step
@@ -350,6 +351,11 @@ def run_ours(args):
             e1.record()
             barrier()
             e2e_passes.append(e0.elapsed_time(e1) / e2e_steps)
+    except Exception as e:  # single GPU only: the device-resident line is still reported, e2e carries the error
+        if dist:
+            raise  # a rank that leaves the collectives early would hang the others
+        e2e_error = f"{type(e).__name__}: {e}"[:300]
+        e2e_passes = [float("nan"), float("nan")]
     finally:
         sys.stderr = _err
     e2e_ms = min(e2e_passes) * steps  # per-step time of the faster pass x `steps`
@@ -431,18 +437,24 @@ def run_ours(args):
                 "also": {"kernel": "score_neg_kernel<FUSED> (fused forward, K2)", "achieved": fwd_gbs,
                          "frac": fwd_gbs / hbm, "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": fwd_ms},
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
-                    "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps,
+            "e2e": {"value": None if e2e_error else e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
+                    "d2h_bytes_per_step": 16, "ms_per_step": None if e2e_error else e2e_ms / steps,
                     "api": "compose.Pipeline.learn(models.*, datasets.Dataset(host, pinned), sampling.NegativeSampling, "
                            "optim.DenseAdam, losses.Adversarial): per step H2D sample+weight, D2H loss sums",
-                    "rolling_loss": e2e_loss, "passes_ms_per_step": e2e_passes_t.tolist(),
-                    "note": "faster of two timed passes of Pipeline.learn over the same K-step dataset"},
+                    "rolling_loss": e2e_loss, "passes_ms_per_step": None if e2e_error else e2e_passes_t.tolist(),
+                    "note": "faster of two timed passes of Pipeline.learn over the same K-step dataset",
+                    **({"error": e2e_error} if e2e_error else {})},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_reference_run(cfg, steps=3, warmup=1, budget_s=20.0, graph=graph)
-            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                base = cpu_reference_run(cfg, steps=3, warmup=1, budget_s=20.0, graph=graph)
+                line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the GPU numbers above must not be lost to a host-side problem
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                        "sample": f"failed: {type(e).__name__}: {e}"[:300]}
             try:  # informative only: must never cost the bench line
                 del trainer, model2, opt, pipe
                 torch.cuda.empty_cache()
