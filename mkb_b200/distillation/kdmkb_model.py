@@ -9,8 +9,7 @@ sampler-to-loss step (``kge_sample_negatives`` / ``kge_filter_pool``, ``kge_fuse
 ``kge_score_fwd`` + ``kge_topk_rows``), ``Evaluation`` on the rank kernels.  The driver around them is host glue
 with the reference's constructor, ``forward``, ``learn`` and printed metrics.
 
-Not provided: ``classification`` datasets (BCE / ConvE mode, outside the KGE hot path) and TransE teachers (the
-reference switches those to its faiss sampler).
+Not provided: ``classification`` datasets (BCE / ConvE mode, outside the KGE hot path).
 """
 from __future__ import annotations
 

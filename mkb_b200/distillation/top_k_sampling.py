@@ -19,7 +19,7 @@ import torch
 
 from .. import ops
 
-__all__ = ["FastTopKSampling", "TopKSampling"]
+__all__ = ["FastTopKSampling", "TopKSampling", "TopKSamplingTransE"]
 
 
 class TopKSampling:
@@ -120,19 +120,17 @@ class FastTopKSampling:
     is the batched kernel path of ``TopKSampling.get`` and the tables are three sorted int64 key vectors with
     their ``[n_keys, k]`` rows on the teacher's device, so ``get`` is three ``searchsorted`` calls.
 
-    A TransE teacher makes the reference switch to its faiss nearest-neighbour sampler
-    (``TopKSamplingTransE``, :168-171), which this package does not provide: that case raises."""
+    A TransE teacher switches the pre-computation to the nearest-neighbour sampler ``TopKSamplingTransE`` like
+    the reference (:168-171)."""
 
     def __init__(self, teacher_entities, teacher_relations, student_entities, student_relations, batch_size_entity,
                  batch_size_relation, n_random_entities, n_random_relations, dataset_teacher, teacher, device="cpu",
                  seed=None, **kwargs):
-        if teacher.name == "TransE":
-            raise NotImplementedError("FastTopKSampling with a TransE teacher uses the reference's faiss sampler "
-                                      "(TopKSamplingTransE), which is outside this package")
-        base = TopKSampling(teacher_entities=teacher_entities, teacher_relations=teacher_relations,
-                            student_entities=student_entities, student_relations=student_relations,
-                            batch_size_entity=batch_size_entity, batch_size_relation=batch_size_relation,
-                            n_random_entities=0, n_random_relations=0, device=device, seed=seed)
+        base_method = TopKSamplingTransE if teacher.name == "TransE" else TopKSampling  # :168-171
+        base = base_method(teacher_entities=teacher_entities, teacher_relations=teacher_relations,
+                           student_entities=student_entities, student_relations=student_relations,
+                           batch_size_entity=batch_size_entity, batch_size_relation=batch_size_relation,
+                           n_random_entities=0, n_random_relations=0, device=device, seed=seed, teacher=teacher)
         self.mapping_entities, self.mapping_relations = base.mapping_entities, base.mapping_relations
         self.batch_size_entity_top_k = batch_size_entity
         self.batch_size_relation_top_k = batch_size_relation
@@ -185,6 +183,86 @@ class FastTopKSampling:
         head_teacher, head_student = self._lookup("head", r * self._span + t)
         relation_teacher, relation_student = self._lookup("relation", h * self._span + t)
         tail_teacher, tail_student = self._lookup("tail", h * self._span + r)
+        if self.n_random_entities > 0:  # _randomize_distribution :894-925, same RNG consumption
+            rnd_t = self._rng.choice(list(self.mapping_entities.keys()), size=self.n_random_entities, replace=False)
+            rnd_s = torch.tensor([[self.mapping_entities[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            head_teacher, head_student = torch.cat([head_teacher, rnd_t], 1), torch.cat([head_student, rnd_s], 1)
+            tail_teacher, tail_student = torch.cat([tail_teacher, rnd_t], 1), torch.cat([tail_student, rnd_s], 1)
+        if self.n_random_relations > 0:  # :927-949
+            rnd_t = self._rng.choice(list(self.mapping_relations.keys()), size=self.n_random_relations, replace=False)
+            rnd_s = torch.tensor([[self.mapping_relations[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)
+            rnd_t = torch.tensor(np.asarray(rnd_t)[None, :], dtype=torch.int64, device=dev).expand(B, -1)
+            relation_teacher = torch.cat([relation_teacher, rnd_t], 1)
+            relation_student = torch.cat([relation_student, rnd_s], 1)
+        return (head_teacher, relation_teacher, tail_teacher, head_student, relation_student, tail_student)
+
+
+class TopKSamplingTransE:
+    """Top-k candidates of a TransE teacher by NEAREST NEIGHBOUR in embedding space instead of by score
+    (mkb/distillation/top_k_sampling.py:680-875): the best heads of ``(h, r, t)`` are the shared entities closest to
+    ``t - r``, the best relations those closest to ``t - h``, the best tails those closest to ``h + r``
+    (``TransE._top_k``), in exact L2 distance over a snapshot of the teacher's rows taken at construction.
+
+    The reference builds that exact search with ``faiss.IndexFlatL2`` (brute force); faiss is not a dependency
+    here: the squared distances of a whole batch against the snapshot are one ``torch.cdist`` on the teacher's
+    device and the selection is ``kge_topk_rows`` (exact, ties by candidate order).  Same constructor, same
+    outputs, same RNG stream for the random extras.  Parity with faiss itself is unpinned (faiss is absent from
+    the build container): the tests pin it to a numpy brute-force search, which is what IndexFlatL2 specifies."""
+
+    def __init__(self, teacher_entities, teacher_relations, student_entities, student_relations, teacher,
+                 batch_size_entity, batch_size_relation, n_random_entities, n_random_relations, seed=None, **kwargs):
+        self.batch_size_entity_top_k = batch_size_entity
+        self.batch_size_relation_top_k = batch_size_relation
+        self.n_random_entities = n_random_entities
+        self.n_random_relations = n_random_relations
+        self._rng = np.random.RandomState(seed)
+        self.mapping_entities = collections.OrderedDict(
+            {i: student_entities[e] for e, i in teacher_entities.items() if e in student_entities})
+        self.mapping_relations = collections.OrderedDict(
+            {i: student_relations[e] for e, i in teacher_relations.items() if e in student_relations})
+        dev = teacher.entity_embedding.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        self._ent_t = torch.tensor(list(self.mapping_entities.keys()), **i64)
+        self._ent_s = torch.tensor(list(self.mapping_entities.values()), **i64)
+        self._rel_t = torch.tensor(list(self.mapping_relations.keys()), **i64)
+        self._rel_s = torch.tensor(list(self.mapping_relations.values()), **i64)
+        with torch.no_grad():  # the "trees": a snapshot, like the rows added to the faiss index (:760-770)
+            self._ent_rows = teacher.entity_embedding.detach()[self._ent_t].clone()
+            self._rel_rows = teacher.relation_embedding.detach()[self._rel_t].clone()
+
+    @property
+    def supervised(self):
+        return False
+
+    @property
+    def batch_size_entity(self):
+        return self.batch_size_entity_top_k + self.n_random_entities
+
+    @property
+    def batch_size_relation(self):
+        return self.batch_size_relation_top_k + self.n_random_relations
+
+    @staticmethod
+    def _nearest(queries, rows, k):
+        """Positions of the ``k`` rows nearest to each query (ascending squared L2 distance)."""
+        d2 = torch.cdist(queries, rows, p=2.0, compute_mode="donot_use_mm_for_euclid_dist").square_()
+        return ops.topk_rows(-d2, k)
+
+    def get(self, sample, teacher, **kwargs):
+        dev = self._ent_rows.device
+        sample = sample.to(dev)
+        B = sample.shape[0]
+        with torch.no_grad():
+            q_head, q_relation, q_tail = teacher._top_k(sample)
+            k_e = min(int(self.batch_size_entity_top_k), self._ent_rows.shape[0])
+            k_r = min(int(self.batch_size_relation_top_k), self._rel_rows.shape[0])
+            top_h = self._nearest(q_head.reshape(B, -1), self._ent_rows, k_e)
+            top_r = self._nearest(q_relation.reshape(B, -1), self._rel_rows, k_r)
+            top_t = self._nearest(q_tail.reshape(B, -1), self._ent_rows, k_e)
+        head_teacher, head_student = self._ent_t[top_h], self._ent_s[top_h]
+        relation_teacher, relation_student = self._rel_t[top_r], self._rel_s[top_r]
+        tail_teacher, tail_student = self._ent_t[top_t], self._ent_s[top_t]
         if self.n_random_entities > 0:  # _randomize_distribution :894-925, same RNG consumption
             rnd_t = self._rng.choice(list(self.mapping_entities.keys()), size=self.n_random_entities, replace=False)
             rnd_s = torch.tensor([[self.mapping_entities[i] for i in rnd_t]], dtype=torch.int64, device=dev).expand(B, -1)

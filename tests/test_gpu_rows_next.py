@@ -361,11 +361,64 @@ def test_fast_top_k_sampling_matches_reference(model):
         unseen = next((h, r, t) for h in range(60) for r in range(7) for t in range(60)
                       if not any(r == b and t == c for _, b, c in train))
         smp.get(sample=torch.tensor([unseen]))
-    with pytest.raises(NotImplementedError):
-        te = models.TransE(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6).to(DEV)
-        distillation.FastTopKSampling(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
-                                      student_relations=rel_s, batch_size_entity=4, batch_size_relation=2,
-                                      n_random_entities=0, n_random_relations=0, teacher=te, dataset_teacher=ds)
+
+
+def _brute_force_transe_neighbours(d, sample, ke, kr):
+    """What faiss.IndexFlatL2 specifies for TopKSamplingTransE (top_k_sampling.py:756-790): exact squared-L2 nearest
+    rows among the shared entities / relations to t - r, t - h, h + r; returns teacher ids."""
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    E, R = d["TransE/ent"].astype(np.float64), d["TransE/rel"].astype(np.float64)
+    se = np.array([i for e, i in ent_t.items() if e in ent_s])
+    sr = np.array([i for r, i in rel_t.items() if r in rel_s])
+    h, r, t = sample[:, 0], sample[:, 1], sample[:, 2]
+
+    def near(q, rows, ids, k):
+        d2 = ((q[:, None, :] - rows[None, :, :]) ** 2).sum(-1)
+        return ids[np.argsort(d2, axis=1, kind="stable")[:, :k]]
+
+    return near(E[t] - R[r], E[se], se, ke), near(E[t] - E[h], R[sr], sr, kr), near(E[h] + R[r], E[se], se, ke)
+
+
+def test_top_k_sampling_transe_is_an_exact_l2_search():
+    """TopKSamplingTransE without faiss: the nearest shared rows in exact L2 distance, student ids through the label
+    maps, the reference's RNG stream for the random extras; and FastTopKSampling picks it for a TransE teacher."""
+    from mkb_b200 import datasets, distillation
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = models.TransE(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6)
+    teacher._set_params(torch.from_numpy(d["TransE/ent"].copy()), torch.from_numpy(d["TransE/rel"].copy()))
+    teacher = teacher.to(DEV)
+    kw = dict(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s, student_relations=rel_s,
+              batch_size_entity=4, batch_size_relation=2, seed=42, teacher=teacher)
+    smp = distillation.TopKSamplingTransE(n_random_entities=2, n_random_relations=1, **kw)
+    sample = d["sample"]
+    ht, rt, tt, hs, rs, ts = (x.cpu().numpy() for x in smp.get(sample=torch.from_numpy(sample), teacher=teacher))
+    want_h, want_r, want_t = _brute_force_transe_neighbours(d, sample, 4, 2)
+    np.testing.assert_array_equal(ht[:, :4], want_h)
+    np.testing.assert_array_equal(rt[:, :2], want_r)
+    np.testing.assert_array_equal(tt[:, :4], want_t)
+    to_s = {i: ent_s[e] for e, i in ent_t.items() if e in ent_s}
+    assert all(to_s[a] == b for a, b in zip(ht.ravel(), hs.ravel())) and ht.shape == (len(sample), 6)
+    rng = np.random.RandomState(42)  # _randomize_distribution: entities first, then relations
+    extra_e = rng.choice(list(to_s.keys()), size=2, replace=False)
+    np.testing.assert_array_equal(ht[:, 4:], np.tile(extra_e, (len(sample), 1)))
+    np.testing.assert_array_equal(tt[:, 4:], np.tile(extra_e, (len(sample), 1)))
+    train = [tuple(int(x) for x in row) for row in d["fast/train"]]
+    ds = datasets.Dataset(train=train, entities=ent_t, relations=rel_t, batch_size=7, shuffle=False, seed=42)
+    fast = distillation.FastTopKSampling(n_random_entities=0, n_random_relations=0, dataset_teacher=ds, **kw)
+    q = np.array(train[2:20:3])
+    got = [x.cpu().numpy() for x in fast.get(sample=torch.from_numpy(q))]
+    want_h, want_r, want_t = _brute_force_transe_neighbours(d, q, 4, 2)
+    np.testing.assert_array_equal(got[0], want_h)
+    np.testing.assert_array_equal(got[1], want_r)
+    np.testing.assert_array_equal(got[2], want_t)
 
 
 def test_kdmkb_model_steps_track_reference():

@@ -429,3 +429,38 @@ def test_pipeline_recognises_only_a_stock_torch_adam():
     # CPU model: never adopted, the generic route raises from the kernels ("CUDA only"), not from the trainer
     pipe = compose.Pipeline(epochs=1)
     assert pipe.adopt_torch_adam and compose.Pipeline(epochs=1, adopt_torch_adam=False).adopt_torch_adam is False
+
+
+def test_top_k_sampling_transe_host_logic(monkeypatch):
+    """TopKSamplingTransE on CPU tensors (row accessor + torch.cdist; only the top-k kernel is replaced by a stable
+    argsort): exact L2 neighbours of t - r, t - h, h + r among the shared rows, as faiss.IndexFlatL2 specifies."""
+    from conftest import load_golden
+    from mkb_b200 import distillation, ops
+
+    d = load_golden("distill_rows.npz")
+    ent_t = {str(e): i for i, e in enumerate(d["labels_t"])}
+    ent_s = {str(e): i for i, e in enumerate(d["labels_s"])}
+    rel_t = {str(r): i for i, r in enumerate(d["rl_t"])}
+    rel_s = {str(r): i for i, r in enumerate(d["rl_s"])}
+    teacher = models.TransE(hidden_dim=8, entities=ent_t, relations=rel_t, gamma=6)
+    teacher._set_params(torch.from_numpy(d["TransE/ent"].copy()), torch.from_numpy(d["TransE/rel"].copy()))
+    monkeypatch.setattr(ops, "topk_rows", lambda s, k: torch.from_numpy(
+        np.argsort(-s.numpy().astype(np.float64), axis=1, kind="stable")[:, :k].copy()))
+    smp = distillation.TopKSamplingTransE(teacher_entities=ent_t, teacher_relations=rel_t, student_entities=ent_s,
+                                          student_relations=rel_s, batch_size_entity=5, batch_size_relation=2,
+                                          n_random_entities=0, n_random_relations=0, seed=1, teacher=teacher)
+    sample = d["sample"]
+    ht, rt, tt, hs, rs, ts = (x.numpy() for x in smp.get(sample=torch.from_numpy(sample), teacher=teacher))
+    E, R = d["TransE/ent"].astype(np.float64), d["TransE/rel"].astype(np.float64)
+    se = np.array([i for e, i in ent_t.items() if e in ent_s])
+    sr = np.array([i for r, i in rel_t.items() if r in rel_s])
+    h, r, t = sample[:, 0], sample[:, 1], sample[:, 2]
+
+    def near(q, rows, ids, k):
+        return ids[np.argsort(((q[:, None, :] - rows[None, :, :]) ** 2).sum(-1), axis=1, kind="stable")[:, :k]]
+
+    np.testing.assert_array_equal(ht, near(E[t] - R[r], E[se], se, 5))
+    np.testing.assert_array_equal(rt, near(E[t] - E[h], R[sr], sr, 2))
+    np.testing.assert_array_equal(tt, near(E[h] + R[r], E[se], se, 5))
+    to_s = {i: ent_s[e] for e, i in ent_t.items() if e in ent_s}
+    assert all(to_s[a] == b for a, b in zip(tt.ravel(), ts.ravel()))
