@@ -150,9 +150,12 @@ class FastTopKSampling:
         for name, key, teacher_rows, student_rows in (("head", r * self._span + t, out[0], out[3]),
                                                       ("relation", h * self._span + t, out[1], out[4]),
                                                       ("tail", h * self._span + r, out[2], out[5])):
-            keys, inverse = torch.unique(key, return_inverse=True)
-            first = torch.full((keys.shape[0],), key.shape[0], dtype=torch.int64, device=dev)
-            first.scatter_reduce_(0, inverse, torch.arange(key.shape[0], device=dev), reduce="amin")
+            keys, inverse = torch.unique(key, return_inverse=True)  # keys come back sorted
+            order = torch.argsort(inverse, stable=True)
+            grouped = inverse[order]
+            starts = torch.ones_like(grouped, dtype=torch.bool)
+            starts[1:] = grouped[1:] != grouped[:-1]
+            first = order[starts]  # one representative triple per key, in key order
             self._tables[name] = (keys, teacher_rows[first], student_rows[first])
 
     @property
