@@ -9,7 +9,7 @@ OUT=gpurun_out
 export PYTHONUNBUFFERED=1
 
 # 1. parity: the whole -m gpu suite (new files: test_gpu_rows_next, test_gpu_sharded, test_gpu_train_byent)
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > $OUT/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -60 > $OUT/pytest_gpu.log  # no -x: the whole picture in one box acquisition
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1
 
 # 2. bench: measured default vs the atomics-free by-entity backward, all four training configs
