@@ -464,3 +464,17 @@ def test_top_k_sampling_transe_host_logic(monkeypatch):
     np.testing.assert_array_equal(tt, near(E[h] + R[r], E[se], se, 5))
     to_s = {i: ent_s[e] for e, i in ent_t.items() if e in ent_s}
     assert all(to_s[a] == b for a, b in zip(tt.ravel(), ts.ravel()))
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under mkb_b200/ may import or execute it (a product path through
+    the oracle or any CPU fallback would void every parity claim)."""
+    pkg = os.path.join(ROOT, "mkb_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "kge_oracle" in text or "torch_port" in text:
+                    offenders.append(os.path.join(dirpath, name))
+    assert not offenders, offenders
