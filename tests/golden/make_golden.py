@@ -592,12 +592,66 @@ def gen_distill_rows():
     print("distill_rows", len(out))
 
 
+def gen_distill_doctests():
+    """The reference's own known answers for the distillation samplers / loss (doctests at
+    distillation/top_k_sampling.py:352-413 and distillation/distillation.py:476-522), re-executed here: the inputs
+    (label maps in dict order, seeded tables, the sample) are stored so the CUDA path can be held to the numbers
+    PRINTED in those docstrings; the asserts below confirm the reference still reproduces them under this torch."""
+    from mkb import distillation
+
+    out = {}
+
+    def maps(prefix, d):
+        out[f"{prefix}/labels"] = np.array(list(d.keys()))
+        out[f"{prefix}/ids"] = np.array(list(d.values()), dtype=np.int64)
+
+    torch.manual_seed(42)
+    dt = datasets.CountriesS1(batch_size=2, seed=42, shuffle=False)
+    dsd = datasets.CountriesS2(batch_size=2, seed=42, shuffle=False)
+    teacher = models.RotatE(entities=dt.entities, relations=dt.relations, gamma=3, hidden_dim=4)
+    maps("topk/ent_t", dt.entities), maps("topk/ent_s", dsd.entities)
+    maps("topk/rel_t", dt.relations), maps("topk/rel_s", dsd.relations)
+    out["topk/ent"], out["topk/rel"] = _np(teacher.entity_embedding).copy(), _np(teacher.relation_embedding).copy()
+    smp = distillation.TopKSampling(teacher_relations=dt.relations, teacher_entities=dt.entities,
+                                    student_entities=dsd.entities, student_relations=dsd.relations, batch_size_entity=4,
+                                    batch_size_relation=1, n_random_entities=1, n_random_relations=0, seed=42)
+    sample = next(iter(dt))["sample"]
+    assert sample.tolist() == [[0, 0, 266], [1, 1, 56]]
+    out["topk/sample"] = _np(sample)
+    res = smp.get(sample=sample, teacher=teacher)
+    assert res[0].tolist() == [[197, 50, 75, 176, 30], [10, 240, 251, 3, 30]]  # top_k_sampling.py:389-391
+    assert res[5].tolist() == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]  # :411-413
+    for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
+        out[f"topk/{k}"] = _np(t)
+
+    torch.manual_seed(42)
+    ds = datasets.Umls(batch_size=3, shuffle=False, seed=42)
+    teacher = models.RotatE(hidden_dim=3, entities=ds.entities, relations=ds.relations, gamma=6)
+    student = models.RotatE(hidden_dim=3, entities=ds.entities, relations=ds.relations, gamma=6)
+    maps("umls/ent", ds.entities), maps("umls/rel", ds.relations)
+    out["umls/t_ent"], out["umls/t_rel"] = _np(teacher.entity_embedding).copy(), _np(teacher.relation_embedding).copy()
+    out["umls/s_ent"], out["umls/s_rel"] = _np(student.entity_embedding).copy(), _np(student.relation_embedding).copy()
+    proc = distillation.Distillation(teacher_entities=ds.entities, student_entities=ds.entities,
+                                     teacher_relations=ds.relations, student_relations=ds.relations,
+                                     sampling=distillation.UniformSampling(batch_size_entity=3, batch_size_relation=3,
+                                                                           seed=42))
+    sample = next(iter(ds))["sample"]
+    out["umls/sample"] = _np(sample)
+    loss = proc.distill(teacher=teacher, student=student, sample=sample)
+    assert round(loss.item(), 4) == 1.3066  # distillation.py:500-501
+    out["umls/loss"] = _np(loss)
+    np.savez_compressed(os.path.join(HERE, "distill_doctests.npz"), **out)
+    print("distill_doctests", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next", "distill"]
+    which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next", "distill", "distilldoc"]
     if "next" in which:
         gen_next_rows()
     if "distill" in which:
         gen_distill_rows()
+    if "distilldoc" in which:
+        gen_distill_doctests()
     if "loader" in which:
         gen_loader_order()
     if "step" in which:

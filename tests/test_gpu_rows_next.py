@@ -462,3 +462,56 @@ def test_kdmkb_model_steps_track_reference():
             upd = getattr(ms[key], name).detach().cpu().numpy() - d[f"kd/{key}/{init}"]
             assert np.abs(upd_ref).max() > 0
             assert (np.abs(upd - upd_ref) > 0.05 * np.abs(upd_ref).max()).mean() < 0.01, (key, name)
+
+
+# --------------------------------------------------------------------------------------------------
+# The reference's OWN known answers for this path: the numbers printed in its doctests
+# --------------------------------------------------------------------------------------------------
+def _label_map(d, prefix):
+    return {str(k): int(v) for k, v in zip(d[f"{prefix}/labels"], d[f"{prefix}/ids"])}
+
+
+def test_top_k_sampling_reproduces_the_reference_doctest():
+    """mkb/distillation/top_k_sampling.py:352-413 (CountriesS1 teacher, CountriesS2 student, RotatE dim 4 under
+    torch.manual_seed(42)): the six tensors printed there, literally."""
+    from mkb_b200 import distillation
+
+    d = load_golden("distill_doctests.npz")
+    ent_t, ent_s = _label_map(d, "topk/ent_t"), _label_map(d, "topk/ent_s")
+    rel_t, rel_s = _label_map(d, "topk/rel_t"), _label_map(d, "topk/rel_s")
+    teacher = models.RotatE(entities=ent_t, relations=rel_t, gamma=3, hidden_dim=4)
+    teacher._set_params(torch.from_numpy(d["topk/ent"].copy()), torch.from_numpy(d["topk/rel"].copy()))
+    teacher = teacher.to(DEV)
+    smp = distillation.TopKSampling(teacher_relations=rel_t, teacher_entities=ent_t, student_entities=ent_s,
+                                    student_relations=rel_s, batch_size_entity=4, batch_size_relation=1,
+                                    n_random_entities=1, n_random_relations=0, seed=42)
+    sample = torch.tensor([[0, 0, 266], [1, 1, 56]])  # :375-377
+    ht, rt, tt, hs, rs, ts = (t.cpu().tolist() for t in smp.get(sample=sample, teacher=teacher))
+    assert ht == [[197, 50, 75, 176, 30], [10, 240, 251, 3, 30]]  # :389-391
+    assert rt == [[0], [1]]  # :393-395
+    assert tt == [[269, 210, 270, 261, 30], [120, 160, 212, 244, 30]]  # :397-399
+    assert hs == [[186, 47, 70, 166, 28], [10, 229, 240, 3, 28]]  # :401-403
+    assert rs == [[0], [1]]  # :405-407
+    assert ts == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]  # :409-413
+
+
+def test_distillation_reproduces_the_reference_doctest():
+    """mkb/distillation/distillation.py:476-501 (Umls, RotatE dim 3 teacher and student under torch.manual_seed(42),
+    UniformSampling(3, 3, seed=42)): ``tensor(1.3066)``."""
+    from mkb_b200 import distillation
+
+    d = load_golden("distill_doctests.npz")
+    ents, rels = _label_map(d, "umls/ent"), _label_map(d, "umls/rel")
+    teacher = models.RotatE(hidden_dim=3, entities=ents, relations=rels, gamma=6)
+    student = models.RotatE(hidden_dim=3, entities=ents, relations=rels, gamma=6)
+    teacher._set_params(torch.from_numpy(d["umls/t_ent"].copy()), torch.from_numpy(d["umls/t_rel"].copy()))
+    student._set_params(torch.from_numpy(d["umls/s_ent"].copy()), torch.from_numpy(d["umls/s_rel"].copy()))
+    teacher, student = teacher.to(DEV), student.to(DEV)
+    proc = distillation.Distillation(teacher_entities=ents, student_entities=ents, teacher_relations=rels,
+                                     student_relations=rels, device=DEV,
+                                     sampling=distillation.UniformSampling(batch_size_entity=3, batch_size_relation=3,
+                                                                           seed=42))
+    loss = proc.distill(teacher=teacher, student=student, sample=torch.from_numpy(d["umls/sample"]))
+    assert round(loss.item(), 4) == 1.3066  # distillation.py:500-501
+    loss.backward()
+    assert student.entity_embedding.grad.abs().sum().item() > 0

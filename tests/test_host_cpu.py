@@ -478,3 +478,29 @@ def test_product_package_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "kge_oracle" in text or "torch_port" in text:
                     offenders.append(os.path.join(dirpath, name))
     assert not offenders, offenders
+
+
+def test_top_k_sampling_host_logic_reproduces_the_reference_doctest(monkeypatch):
+    """The tensors printed at mkb/distillation/top_k_sampling.py:389-413, from the oracle scorer + a stable argsort
+    through this package's TopKSampling (candidate maps, chunking, RNG stream)."""
+    from conftest import load_golden
+    from mkb_b200 import distillation, ops
+
+    d = load_golden("distill_doctests.npz")
+
+    def label_map(prefix):
+        return {str(k): int(v) for k, v in zip(d[f"{prefix}/labels"], d[f"{prefix}/ids"])}
+
+    teacher = _OracleModel("RotatE", d["topk/ent"].astype(np.float64), d["topk/rel"].astype(np.float64), 3.0)
+    monkeypatch.setattr(ops, "topk_rows", lambda s, k: torch.from_numpy(
+        np.argsort(-s.numpy().astype(np.float64), axis=1, kind="stable")[:, :k].copy()))
+    smp = distillation.TopKSampling(teacher_relations=label_map("topk/rel_t"), teacher_entities=label_map("topk/ent_t"),
+                                    student_entities=label_map("topk/ent_s"), student_relations=label_map("topk/rel_s"),
+                                    batch_size_entity=4, batch_size_relation=1, n_random_entities=1,
+                                    n_random_relations=0, seed=42)
+    ht, rt, tt, hs, rs, ts = (t.tolist() for t in smp.get(sample=torch.tensor([[0, 0, 266], [1, 1, 56]]), teacher=teacher))
+    assert ht == [[197, 50, 75, 176, 30], [10, 240, 251, 3, 30]]
+    assert tt == [[269, 210, 270, 261, 30], [120, 160, 212, 244, 30]]
+    assert hs == [[186, 47, 70, 166, 28], [10, 229, 240, 3, 28]]
+    assert ts == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]
+    assert rt == rs == [[0], [1]]
