@@ -515,3 +515,20 @@ def test_distillation_reproduces_the_reference_doctest():
     assert round(loss.item(), 4) == 1.3066  # distillation.py:500-501
     loss.backward()
     assert student.entity_embedding.grad.abs().sum().item() > 0
+
+
+def test_utils_top_k_reproduces_the_reference_doctest():
+    """mkb/utils/top_k.py:24-57 (CountriesS1, RotatE dim 4 under torch.manual_seed(42) — the same tables as the
+    TopKSampling doctest): the label lists printed there, through the positives kernel + the exact top-k kernel."""
+    d = load_golden("distill_doctests.npz")
+    ents, rels = _label_map(d, "topk/ent_t"), _label_map(d, "topk/rel_t")
+    model = models.RotatE(entities=ents, relations=rels, gamma=3, hidden_dim=4)
+    model._set_params(torch.from_numpy(d["topk/ent"].copy()), torch.from_numpy(d["topk/rel"].copy()))
+    model = model.to(DEV)
+    top_k = utils.TopK(entities=ents, relations=rels)
+    assert top_k.top_heads(k=4, model=model, relation="neighbor", tail="western_africa") == [
+        "mauritius", "são_tomé_and_príncipe", "guinea-bissau", "saint_kitts_and_nevis"]  # top_k.py:35-41
+    assert top_k.top_relations(k=4, model=model, head="azerbaijan", tail="western_africa") == [
+        "locatedin", "neighbor"]  # :43-49
+    assert top_k.top_tails(k=4, model=model, head="western_africa", relation="neighbor") == [
+        "afghanistan", "barbados", "taiwan", "new_caledonia"]  # :51-57
