@@ -219,7 +219,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = args.config
-    base = cpu_reference_run(cfg, args.steps, args.warmup, budget_s=150.0)
+    base = cpu_reference_run(cfg, args.steps, args.warmup, budget_s=args.cpu_budget)
     ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -476,6 +476,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=150.0,
+                    help="--impl reference: seconds of CPU work the bounded sample is sized for (all steps together)")
     ap.add_argument("--mode", default=None, choices=["colpar", "allreduce", "rowshard"],
                     help="multi-GPU scheme of DeviceTrainer (default colpar: column-parallel backward + fused "
                          "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce; rowshard: "

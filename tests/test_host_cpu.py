@@ -504,3 +504,30 @@ def test_top_k_sampling_host_logic_reproduces_the_reference_doctest(monkeypatch)
     assert hs == [[186, 47, 70, 166, 28], [10, 229, 240, 3, 28]]
     assert ts == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]
     assert rt == rs == [[0], [1]]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU operator sequence on the host cores, no GPU involved):
+    one JSON line with the own arm's metric / unit / config plus impl, cpu_baseline and a zero-copy e2e object."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg1",
+                        "--steps", "2", "--warmup", "1", "--cpu-budget", "3"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"].startswith("training triples/sec")
+    assert line["unit"] == "triples/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1 and line["dtype"] == "f32"
+    assert "Wn18rr" in line["config"]["workload"] and "TransE" in line["config"]["workload"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "positives" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 exit 0 without work (the driver launches the arm under torchrun for N > 1)
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
