@@ -531,3 +531,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1"))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("variant", (("RotatE", "scatter", "0", "independent", "0"),  # the default step
+                                     ("ComplEx", "scatter", "0", "reference", "1")))  # pooled GEMM flow
+def test_bench_own_arm_line_contract_on_the_emulation(variant):
+    """bench.py's own arm end to end (DeviceTrainer loop, Pipeline.learn e2e arm, JSON line) on the CPU emulation
+    of the kernels with a toy config — tests/emu/bench_dryrun.py; timings are fake, the plumbing and the line are
+    real: every key of the bench contract is present and the launch count is the step's kernel count."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "bench_dryrun.py"), *variant],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["unit"] == "triples/s" and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["data"] == "synthetic" and line["dtype"] == "f32" and line["n_gpus"] == 1 and line["warmup"] >= 3
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["unit"] == "GB/s"
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] == 8 * 3 * 8 + 8 * 4 and line["e2e"]["d2h_bytes_per_step"] == 16
+    assert "error" not in line["e2e"] and line["e2e"]["value"] > 0
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
+    assert "workload" in line["config"] and "model" not in line["config"]
+    if variant[1] == "scatter" and variant[4] == "0":
+        assert line["gpu_launches"] == 5 * line["steps"]  # sampler, fused fwd, fused bwd, adam(entity), adam(relation)
+    else:
+        assert line["gpu_launches"] > 0
