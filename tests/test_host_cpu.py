@@ -564,3 +564,14 @@ def test_bench_own_arm_line_contract_on_the_emulation(variant):
         assert line["gpu_launches"] == 5 * line["steps"]  # sampler, fused fwd, fused bwd, adam(entity), adam(relation)
     else:
         assert line["gpu_launches"] > 0
+
+
+def test_graft_entry_smoke_on_the_emulation():
+    """__graft_entry__.smoke() (one fused training step per model and mode + filtered ranking, checked against the
+    oracle) through the unchanged package on the emulated kernels — tests/emu/smoke_dryrun.py."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "smoke_dryrun.py")], capture_output=True,
+                       text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
