@@ -15,14 +15,20 @@ SUBSET = ("test_fused_step_vs_oracle or test_sharded_kernels_equal_unsharded or 
           "test_protate_fused or test_rank_tile or test_sharded_rank_counts or test_unfused_loss")
 
 
+# the random schedule is ~3x slower per test (warps sit rounds out): the kernel families with shared-memory
+# hand-offs, sorts and tickets; the full six-seed run over everything is a recipe, not part of CI
+RANDOM_SUBSET = ("test_fused_step_vs_oracle or test_samplers_bit_exact or test_topk_rows or test_by_entity or "
+                 "test_pooled_dot or test_chunked_and_multi_record or test_kl_divergence")
+
+
 def test_emulation_suite_is_schedule_independent():
     procs = []
-    for order, seed in (("reverse", 0), ("random", 1)):  # both at once: the box has cores to spare
+    for order, seed, subset in (("reverse", 0, SUBSET), ("random", 1, RANDOM_SUBSET)):  # both at once
         env = dict(os.environ, KGE_EMU_ORDER=order, KGE_EMU_SEED=str(seed))
         env.pop("KGE_TEST_EMU", None)
         procs.append((order, subprocess.Popen(
             [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emu_kernels.py"), "-q", "-x", "-p",
-             "no:cacheprovider", "-k", SUBSET], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+             "no:cacheprovider", "-k", subset], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
             text=True)))
     for order, pr in procs:
         out, _ = pr.communicate(timeout=1500)
