@@ -33,7 +33,7 @@ _GPU_FILE_ORDER = ("test_gpu_parity", "test_gpu_multi", "test_gpu_rows_next", "t
 
 def pytest_collection_modifyitems(config, items):
     def key(item):
-        mod = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        mod = os.path.splitext(os.path.basename(str(getattr(item, "path", None) or item.fspath)))[0]
         rank = _GPU_FILE_ORDER.index(mod) if mod in _GPU_FILE_ORDER else -1  # CPU files keep their place, first
         return (rank, "pooled_gemm" in item.name)
 
