@@ -532,3 +532,18 @@ def test_utils_top_k_reproduces_the_reference_doctest():
         "locatedin", "neighbor"]  # :43-49
     assert top_k.top_tails(k=4, model=model, head="western_africa", relation="neighbor") == [
         "afghanistan", "barbados", "taiwan", "new_caledonia"]  # :51-57
+
+
+@pytest.mark.parametrize("pool", ("independent", "reference"))
+def test_pipeline_adopts_a_stock_torch_adam(pool):
+    """The reference quick-start's own objects — a stock torch.optim.Adam over the model's parameters — are taken
+    over by the device-resident step: same trained tables and loss as the generic three-call route with the same
+    optimizer stepping through autograd; optimizer.state stays current (step count, moments)."""
+    from test_gpu_parity import _toy_pipeline
+
+    ref, p0 = _toy_pipeline("generic", pool)
+    m, p = _toy_pipeline("adopted", pool)  # asserts adoption and the optimizer state inside
+    torch.testing.assert_close(m.entity_embedding, ref.entity_embedding, rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(m.relation_embedding, ref.relation_embedding, rtol=2e-3, atol=2e-4)
+    assert abs(p.metric_loss.get() - p0.metric_loss.get()) < 1e-4
+    assert abs(p.test_scores["MR"] - p0.test_scores["MR"]) <= 1.0
