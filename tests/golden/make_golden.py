@@ -623,6 +623,15 @@ def gen_distill_doctests():
     assert res[5].tolist() == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]  # :411-413
     for k, t in zip(("ht", "rt", "tt", "hs", "rs", "ts"), res):
         out[f"topk/{k}"] = _np(t)
+    # FastTopKSampling doctest (:24-81): same teacher and sample, tables pre-computed over CountriesS1's training set
+    out["topk/train"] = np.array(dt.train, dtype=np.int64)
+    fast = distillation.FastTopKSampling(teacher_relations=dt.relations, teacher_entities=dt.entities,
+                                         student_entities=dsd.entities, student_relations=dsd.relations,
+                                         batch_size_entity=4, batch_size_relation=1, n_random_entities=1,
+                                         n_random_relations=0, seed=42, teacher=teacher, dataset_teacher=dt)
+    res = fast.get(sample=sample, teacher=teacher)
+    assert res[0].tolist() == [[197, 50, 75, 176, 30], [10, 240, 251, 3, 30]]  # :53-55
+    assert res[5].tolist() == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]  # :77-79
 
     torch.manual_seed(42)
     ds = datasets.Umls(batch_size=3, shuffle=False, seed=42)

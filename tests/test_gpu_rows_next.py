@@ -547,3 +547,28 @@ def test_pipeline_adopts_a_stock_torch_adam(pool):
     torch.testing.assert_close(m.relation_embedding, ref.relation_embedding, rtol=2e-3, atol=2e-4)
     assert abs(p.metric_loss.get() - p0.metric_loss.get()) < 1e-4
     assert abs(p.test_scores["MR"] - p0.test_scores["MR"]) <= 1.0
+
+
+def test_fast_top_k_sampling_reproduces_the_reference_doctest():
+    """mkb/distillation/top_k_sampling.py:24-81: the same six tensors from tables pre-computed over CountriesS1's
+    1 111 training triples (batched kernel path here, a per-triple Python loop in the reference)."""
+    from mkb_b200 import datasets, distillation
+
+    d = load_golden("distill_doctests.npz")
+    ent_t, ent_s = _label_map(d, "topk/ent_t"), _label_map(d, "topk/ent_s")
+    rel_t, rel_s = _label_map(d, "topk/rel_t"), _label_map(d, "topk/rel_s")
+    teacher = models.RotatE(entities=ent_t, relations=rel_t, gamma=3, hidden_dim=4)
+    teacher._set_params(torch.from_numpy(d["topk/ent"].copy()), torch.from_numpy(d["topk/rel"].copy()))
+    teacher = teacher.to(DEV)
+    train = [tuple(int(x) for x in row) for row in d["topk/train"]]
+    ds = datasets.Dataset(train=train, entities=ent_t, relations=rel_t, batch_size=2, shuffle=False, seed=42)
+    smp = distillation.FastTopKSampling(teacher_relations=rel_t, teacher_entities=ent_t, student_entities=ent_s,
+                                        student_relations=rel_s, batch_size_entity=4, batch_size_relation=1,
+                                        n_random_entities=1, n_random_relations=0, seed=42, teacher=teacher,
+                                        dataset_teacher=ds)
+    ht, rt, tt, hs, rs, ts = (t.cpu().tolist() for t in smp.get(sample=torch.tensor([[0, 0, 266], [1, 1, 56]])))
+    assert ht == [[197, 50, 75, 176, 30], [10, 240, 251, 3, 30]]  # :53-55
+    assert rt == [[0], [1]] and rs == [[0], [1]]  # :57-59, :69-71
+    assert tt == [[269, 210, 270, 261, 30], [120, 160, 212, 244, 30]]  # :61-63
+    assert hs == [[186, 47, 70, 166, 28], [10, 229, 240, 3, 28]]  # :65-67
+    assert ts == [[269, 198, 270, 256, 28], [111, 149, 201, 234, 28]]  # :73-79
