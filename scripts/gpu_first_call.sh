@@ -38,5 +38,12 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:byen
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:score_bwd_kernel -s 6 -c 1 \
     -o $OUT/ncu_dq_pass python bench.py --steps 3 --warmup 3 --no-cpu-baseline --backward by_entity \
     > $OUT/ncu_dq_pass.log 2>&1
+# the default (scatter) step: one full capture of every kernel of a step (sampler, fwd, bwd, adam x2)
+timeout 400 ncu --set full --clock-control none --import-source on --launch-skip 40 --launch-count 10 \
+    -o $OUT/ncu_default_step python bench.py --steps 3 --warmup 8 --no-cpu-baseline \
+    > $OUT/ncu_default_step.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --launch-skip 40 --launch-count 10 \
+    -o $OUT/ncu_cfg4_step python bench.py --config cfg4 --steps 3 --warmup 8 --no-cpu-baseline \
+    > $OUT/ncu_cfg4_step.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/nvidia_smi.csv
 ls -la $OUT
