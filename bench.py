@@ -13,11 +13,12 @@ loop body of mkb/compose/pipeline.py:206-242, on a synthetic batch of the named 
             copies and the loss read-back inside the timed region;
   * roofline : the dominant kernel (fused backward), algorithmic bytes / CUDA-event time measured
             inside the timed region vs the measured HBM peak in MEASURED_PEAKS.json;
-  * cpu_baseline : the reference's eager-PyTorch CPU operator sequence (oracle/torch_port.py, bit-exact
-            with the reference on the golden vectors) timed on this box's host cores on a bounded
-            sample of the same workload (rank 0, N=1 only).
+  * cpu_baseline : the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh) driven
+            through its own mkb.compose.Pipeline.learn on this box's host cores on a bounded sample of
+            the same workload (rank 0, N=1 only); oracle/torch_port.py if baseline/_ref is absent.
+  * reference_on_this_gpu : the same unmodified reference with device='cuda', full batch.
 
-Reference arm (--impl reference): that same CPU port, all host threads, bounded sample per step.
+Reference arm (--impl reference): that same reference run, all host threads, bounded sample per step.
 """
 from __future__ import annotations
 
@@ -137,10 +138,99 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's eager-PyTorch CPU path (oracle port)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, steps, warmup, budget_s, graph=None):
-    """Times oracle/torch_port.CpuTrainer (loop body of compose/pipeline.py:206-242: reference sampler,
-    two forwards, loss, backward, dense Adam) on a bounded sample: the first B_s positives of each
-    batch with all K negatives, B_s chosen so (steps+warmup) steps fit in ``budget_s`` seconds."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # the unmodified reference, installed by baseline/install_ref.sh
+
+
+def _import_reference():
+    """The unmodified reference package (raphaelsty/mkb) from the git-ignored baseline/_ref (it travels to the
+    GPU box with gpurun).  Returns the module or None when it was never installed."""
+    if not os.path.isdir(os.path.join(REF_DIR, "mkb")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import mkb  # noqa: F401
+
+        return mkb
+    except Exception:
+        return None
+
+
+class _Quiet:
+    """Pipeline.learn prints its epoch banner to stdout and a tqdm bar to stderr; the bench prints ONE line."""
+
+    def __enter__(self):
+        self._o, self._e = sys.stdout, sys.stderr
+        sys.stdout = sys.stderr = open(os.devnull, "w")
+
+    def __exit__(self, *a):
+        sys.stdout.close()
+        sys.stdout, sys.stderr = self._o, self._e
+
+
+def reference_run(cfg, steps, warmup, budget_s, graph=None, device="cpu", full_batch=False):
+    """Times the UNMODIFIED reference through its own public API — mkb.compose.Pipeline.learn over a
+    mkb.datasets.Dataset with mkb.models.*, mkb.sampling.NegativeSampling, mkb.losses.Adversarial and
+    torch.optim.Adam (compose/pipeline.py:202-244) — on a bounded sample of the config: batches of the first
+    B_s positives (all K negatives each), B_s sized so that (steps + warmup) steps fit in ``budget_s`` seconds
+    (B_s = B when that fits).  Wall clock around ``learn`` (it ends every step with ``error.item()``)."""
+    mkb = _import_reference()
+    if mkb is None:
+        return None
+    from mkb import compose as rcompose, datasets as rdatasets, losses as rlosses, models as rmodels
+    from mkb import sampling as rsampling
+
+    ds, mname, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    cores = torch.get_num_threads()
+    graph = synth_graph(cfg) if graph is None else graph
+    tri = [tuple(r) for r in graph.tolist()]
+    ents, rels = {i: i for i in range(N)}, {i: i for i in range(R)}
+    torch.manual_seed(42)
+    model = getattr(rmodels, mname)(hidden_dim=D, entities=ents, relations=rels, gamma=gamma).to(device)
+    sampler = rsampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=42)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=5e-5)
+    loss = rlosses.Adversarial(alpha=0.5)
+    pick = np.random.RandomState(1)
+
+    def learn(bs, n_steps):
+        pairs = max(1, (n_steps + 1) // 2)  # one epoch of Dataset = a head-batch and a tail-batch per bs triples
+        rows = [tri[i] for i in pick.choice(len(tri), bs * pairs, replace=False)]
+        data = rdatasets.Dataset(train=rows, entities=ents, relations=rels, batch_size=bs, shuffle=False,
+                                 seed=None, num_workers=0)
+        pipe = rcompose.Pipeline(epochs=1, device=device)
+        with _Quiet():
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.learn(model=model, dataset=data, sampling=sampler, optimizer=opt, loss=loss)
+            if device != "cpu":
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        return dt, 2 * pairs
+
+    if full_batch:
+        bs = B
+    else:
+        learn(2, 2)  # first touch of the allocator / thread pool
+        dt, n = learn(4, 2)
+        per_row = dt / (4 * n)
+        bs = int(max(2, min(B, budget_s / max(steps + warmup, 1) / max(per_row, 1e-6))))
+    if warmup:
+        learn(bs, warmup)
+    t, n = learn(bs, steps)
+    return {
+        "value": bs * (1 + K) * n / t, "unit": UNIT, "cores": cores, "kind": "reference",
+        "sample": f"{n} steps x {'all' if bs == B else 'first'} {bs} of {B} positives per batch, all {K} negatives "
+                  f"each, D={D}: unmodified mkb {mkb.__version__} (baseline/_ref) driven through "
+                  f"mkb.compose.Pipeline.learn — Dataset, NegativeSampling.generate, {mname}.forward x2, Adversarial, "
+                  f"backward, torch.optim.Adam — torch {torch.__version__} on {device}, {cores} host threads",
+        "ms_per_step": 1e3 * t / n, "batch": bs, "steps_run": n,
+    }
+
+
+def port_run(cfg, steps, warmup, budget_s, graph=None):
+    """Fallback when baseline/_ref is absent: oracle/torch_port.CpuTrainer (the reference's ATen operator
+    sequence, bit-exact with it on the golden vectors) on the same bounded sample."""
     from oracle import torch_port as tp
 
     ds, model, N, R, T, D, B, K, gamma = CONFIGS[cfg]
@@ -176,9 +266,15 @@ def cpu_reference_run(cfg, steps, warmup, budget_s, graph=None):
         "value": value, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": f"{steps} steps x first {bs} of {B} positives per batch, all {K} negatives each, D={D}: "
                   f"reference sampler + 2 forwards + loss + backward + dense Adam (oracle/torch_port.py, "
-                  f"torch {torch.__version__} CPU, {cores} threads)",
-        "ms_per_step": 1e3 * t / steps,
+                  f"torch {torch.__version__} CPU, {cores} threads; baseline/_ref not installed)",
+        "ms_per_step": 1e3 * t / steps, "batch": bs, "steps_run": steps,
     }
+
+
+def cpu_reference_run(cfg, steps, warmup, budget_s, graph=None):
+    """The reference arm / CPU baseline: the unmodified reference when baseline/_ref is installed, else the port."""
+    out = reference_run(cfg, steps, warmup, budget_s, graph=graph)
+    return out if out is not None else port_run(cfg, steps, warmup, budget_s, graph=graph)
 
 
 def eager_gpu_run(cfg, graph, dev, steps=5, warmup=2):
@@ -461,6 +557,16 @@ def run_ours(args):
                 line["cpu_baseline"]["same_operators_on_this_gpu"] = eager_gpu_run(cfg, graph, dev)
             except Exception as e:  # e.g. out of memory for the eager path's [B,K,2D] temporaries
                 line["cpu_baseline"]["same_operators_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            try:  # the unmodified reference with device='cuda', full batch, through its own Pipeline.learn
+                torch.cuda.empty_cache()
+                r = reference_run(cfg, steps=6, warmup=2, budget_s=0, graph=graph, device=str(dev), full_batch=True)
+                if r is not None:
+                    line["reference_on_this_gpu"] = {
+                        **{k: r[k] for k in ("value", "unit", "ms_per_step", "sample")},
+                        "ours_over_it": {"value": value / r["value"],
+                                         "e2e": None if e2e_error else e2e_value / r["value"]}}
+            except Exception as e:
+                line["reference_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line))
     if dist:
         torch.distributed.barrier()

@@ -108,13 +108,35 @@ class Pipeline:
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         key = (id(model), id(sampling), id(optimizer), float(loss.alpha), int(dataset.batch_size), multi)
         if getattr(self, "_trainer_key", None) != key:  # keep buffers across learn() calls
+            # multi-rank: every batch of the dataset is the GLOBAL batch; rank r trains on its r-th slice
+            per_rank = -(-int(dataset.batch_size) // dist.get_world_size()) if multi else int(dataset.batch_size)
             self._trainer = DeviceTrainer.from_optimizer(model, sampling, optimizer, alpha=loss.alpha,
-                                                         max_batch=int(dataset.batch_size), distributed=multi,
+                                                         max_batch=per_rank, distributed=multi,
                                                          **self.trainer_options)
             self._trainer_key = key
+        # hyper-parameters are re-read on every learn() call and every epoch (_learn_on_device): an LR scheduler
+        # or an edit of optimizer.param_groups[0] between epochs takes effect like it does in the reference
+        self._trainer.adopt_hyper_parameters(optimizer)
         return self._trainer
 
-    def _learn_on_device(self, trainer, dataset, epoch):
+    @staticmethod
+    def _rank_slice(sample, weight, trainer):
+        """Rank r's share of a global batch: the r-th block of ceil(B / world) rows.  Short blocks (B not a
+        multiple of world, or the epoch's last batch) are padded with copies of row 0 at weight 0 — such rows
+        add nothing to the loss sums or to any gradient (every term carries the positive's weight), and all
+        ranks keep the same local batch size, which the column-parallel record exchange relies on."""
+        world, rank = trainer.world, trainer.rank
+        B = sample.shape[0]
+        per = -(-B // world)
+        lo, hi = min(rank * per, B), min((rank + 1) * per, B)
+        s, w = sample[lo:hi], weight[lo:hi]
+        if hi - lo < per:
+            pad = per - (hi - lo)
+            s = torch.cat([s, sample[:1].expand(pad, -1)])
+            w = torch.cat([w, torch.zeros(pad, dtype=weight.dtype, device=weight.device)])
+        return s.contiguous(), w.contiguous()
+
+    def _learn_on_device(self, trainer, dataset, epoch, optimizer=None):
         """Device-resident epoch: per batch two async H2D copies (skipped when the dataset already
         lives on the GPU), five kernel launches, and an async D2H copy of the loss sums into pinned
         memory that is read one step later (the reference's ``error.item()`` without the stall)."""
@@ -122,10 +144,15 @@ class Pipeline:
         host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         pending = None
+        if optimizer is not None:
+            trainer.adopt_hyper_parameters(optimizer)
         bar = Bar(dataset=dataset, update_every=10)
         for k, data in enumerate(bar):
-            sample = data["sample"].to(dev, non_blocking=True)
-            weight = data["weight"].to(dev, non_blocking=True)
+            sample, weight = data["sample"], data["weight"]
+            if trainer.distributed:
+                sample, weight = self._rank_slice(sample, weight, trainer)
+            sample = sample.to(dev, non_blocking=True)
+            weight = weight.to(dev, non_blocking=True)
             stats = trainer.step(sample, weight, data["mode"])
             host[k & 1].copy_(stats, non_blocking=True)
             done[k & 1].record()
@@ -149,7 +176,7 @@ class Pipeline:
         step = 0
         for epoch in range(self.epochs):
             if trainer is not None:
-                self._learn_on_device(trainer, dataset, epoch)
+                self._learn_on_device(trainer, dataset, epoch, optimizer)
             bar = Bar(dataset=dataset if trainer is None else [], update_every=10)
             for data in bar:
                 sample = data["sample"].to(self.device)

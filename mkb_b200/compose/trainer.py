@@ -88,6 +88,11 @@ class DeviceTrainer:
             t.sync_optimizer_state()
         return t
 
+    def adopt_hyper_parameters(self, optimizer):
+        """Re-read lr / betas / eps from the optimizer's param group (LR schedulers, manual edits)."""
+        g = optimizer.param_groups[0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"])
+
     def sync_optimizer_state(self):
         opt = getattr(self, "_optimizer", None)
         if opt is not None:
@@ -156,6 +161,8 @@ class DeviceTrainer:
                               device=self.dev)
         self._csr = {m: sampling._csr("head" if m == "head-batch" else "tail", self.dev)
                      for m in ("head-batch", "tail-batch")}
+        # every rank draws its own negatives: the same user seed, a rank-specific Philox key
+        self._seed = (int(sampling.seed) + 0x9E3779B97F4A7C15 * self.rank) & (2 ** 64 - 1)
         self.t = 0
         self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd] CUDA events (bench.py)
 
@@ -172,9 +179,12 @@ class DeviceTrainer:
             self._setup_colpar(f32)
         else:
             # one flat buffer for both gradients => a single all-reduce in the allreduce mode
-            self._gflat = torch.zeros(self.ent.numel() + self.rel.numel(), **f32)
+            # (the relation part starts on a 16-byte boundary: kge_adam_step / the vector REDs need aligned
+            # pointers, and N*dim is not a multiple of 4 for e.g. TransE dim 50 x 14 541 entities)
+            rel_off = (self.ent.numel() + 3) // 4 * 4
+            self._gflat = torch.zeros(rel_off + self.rel.numel(), **f32)
             self.g_ent = self._gflat[: self.ent.numel()].view_as(self.ent)
-            self.g_rel = self._gflat[self.ent.numel():].view_as(self.rel)
+            self.g_rel = self._gflat[rel_off: rel_off + self.rel.numel()].view_as(self.rel)
             self.m_ent, self.v_ent = torch.zeros_like(self.ent), torch.zeros_like(self.ent)
             self.m_rel, self.v_rel = torch.zeros_like(self.rel), torch.zeros_like(self.rel)
             self.neg = torch.empty((max_batch, K), dtype=torch.int64, device=self.dev)
@@ -372,7 +382,7 @@ class DeviceTrainer:
             ops.filter_pool(self._csr[mode], sample, mode, self.K, s.n_entity, pool, self.status, neg,
                             positions=self.neg_pos[: sample.shape[0]] if self.pooled_gemm else None)
         else:
-            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, s.seed, s._calls, self.status,
+            ops.sample_negatives(self._csr[mode], sample, mode, self.K, s.n_entity, self._seed, s._calls, self.status,
                                  neg, sort_rows=s.sort_rows)
         s._calls += 1
 

@@ -43,10 +43,14 @@ class NegativeSampling:
         self.size = size
         self.n_entity = len(entities)
         self.n_relation = len(relations)
-        self.seed = seed
+        # seed=None is legal in the reference (np.random.RandomState(None), negative_sampling.py:151; KdmkbModel's
+        # default): resolve it once to a concrete value so the device Philox key and the RandomState agree
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy) & (2 ** 32 - 1)
+        self.seed = int(seed)
         self.pool = pool
         self.sort_rows = sort_rows  # independent pool only: rows ascending by id (L2-friendly gathers)
-        self._rng = np.random.RandomState(seed)
+        self._rng = np.random.RandomState(self.seed)
         self._calls = 0
         self._host_csr = {side: build_filter_csr(train_triples, self.n_entity, side) for side in ("head", "tail")}
         self._dev_csr = {}

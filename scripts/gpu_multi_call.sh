@@ -8,10 +8,13 @@ OUT=gpurun_out
 export PYTHONUNBUFFERED=1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_sharded.py -m gpu -q -x 2>&1 | tail -30 > $OUT/pytest_multi_${N}gpu.log
+nvidia-smi topo -m > $OUT/topo_${N}gpu.txt 2>&1
 for cfg in cfg2 cfg4; do
   for mode in colpar rowshard allreduce; do
+    nvidia-smi nvlink -gt d -i 0 > $OUT/nvlink_${cfg}_${N}gpu_${mode}_before.txt 2>&1
     timeout 300 $RUN bench.py --gpus $N --config $cfg --steps 100 --warmup 10 --mode $mode \
         > $OUT/bench_${cfg}_${N}gpu_${mode}.json 2> $OUT/bench_${cfg}_${N}gpu_${mode}.err
+    nvidia-smi nvlink -gt d -i 0 > $OUT/nvlink_${cfg}_${N}gpu_${mode}_after.txt 2>&1
   done
 done
 NCCL_DEBUG=INFO timeout 200 $RUN bench.py --gpus $N --config cfg4 --steps 5 --warmup 3 --mode rowshard \

@@ -653,8 +653,84 @@ def gen_distill_doctests():
     print("distill_doctests", len(out))
 
 
+CFG5_MARGINS = (1e-6, 1e-5, 1e-4)  # relative to max(|s_pos|, mean|s|), see oracle rank_all
+
+
+def gen_cfg5_cases(n_queries=64, n_queries_rotate=32):
+    """BASELINE config 5 AT SIZE: the reference's own filtered ranks on the real Wn18rr (N = 40 943, 11
+    relations, filter = train + valid + test) at D = 1000, from its unmodified Evaluation.compute_score
+    (evaluation/evaluation.py:217-279 over datasets/base.py:196-241's candidate / filter_bias lists).
+    Tables are rebuilt from a seed on both sides (tests/golden/cfg5_tables.py).  Per model: the queries,
+    the reference's fp32 ranks for both modes, the fp64 oracle's ranks and, per query, how many unfiltered
+    candidates lie within 1e-6 / 1e-5 / 1e-4 (relative) of the positive's score (the near-ties an fp32 implementation with a
+    different summation order may legitimately flip)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), ".."))
+    sys.path.insert(0, HERE)
+    import cfg5_tables
+    from oracle import kge_oracle as ko
+    from river import stats as rstats
+
+    class Rec(rstats.Mean):
+        def __init__(self):
+            super().__init__()
+            self.seen = []
+
+        def update(self, x):
+            self.seen.append(x)
+            return super().update(x)
+
+    ds = datasets.Wn18rr(batch_size=1, shuffle=False, pre_compute=False, seed=42)
+    N, R, D = ds.n_entity, ds.n_relation, 1000
+    train = np.array(ds.train, dtype=np.int64)
+    true_triples = ds.train + ds.valid + ds.test
+    all_true = np.array(true_triples, dtype=np.int64)
+    hc, tc = ko.build_filter_csr(all_true, N, "head"), ko.build_filter_csr(all_true, N, "tail")
+    out = {"n_entity": np.int64(N), "n_relation": np.int64(R), "hidden_dim": np.int64(D),
+           "train": train.astype(np.int32), "valid": np.array(ds.valid, dtype=np.int32),
+           "test": np.array(ds.test, dtype=np.int32)}
+    pick = np.random.RandomState(5).permutation(len(ds.test))
+    for name, gamma in MODEL_GAMMA.items():
+        nq = n_queries_rotate if name == "RotatE" else n_queries
+        queries = [ds.test[i] for i in pick[:nq]]
+        ent, rel = cfg5_tables.make_tables(name, train, N, R, D, gamma)
+        model = getattr(models, name)(hidden_dim=D, entities=ds.entities, relations=ds.relations, gamma=gamma)
+        with torch.no_grad():
+            model.entity_embedding.copy_(torch.from_numpy(ent))
+            model.relation_embedding.copy_(torch.from_numpy(rel))
+        ev = evaluation.Evaluation(entities=ds.entities, relations=ds.relations, batch_size=2,
+                                   true_triples=true_triples, num_workers=0)
+        metrics = collections.OrderedDict({m: Rec() for m in ["MRR", "MR", "HITS@1", "HITS@3", "HITS@10"]})
+        import time as _t
+        t0 = _t.time()
+        with torch.no_grad():
+            for stream in ev.get_entity_stream(queries):  # head-batch stream, then tail-batch stream
+                metrics = ev.compute_score(model=model, test_set=stream, metrics=metrics, device="cpu")
+        ranks = np.array(metrics["MR"].seen, dtype=np.int64).reshape(2, nq)  # [head-batch, tail-batch]
+        t_ref = _t.time() - t0
+        out[f"{name}/queries"] = np.array(queries, dtype=np.int64)
+        out[f"{name}/gamma"] = np.float64(gamma)
+        out[f"{name}/ref_ranks"] = ranks
+        out[f"{name}/ref_metrics"] = np.array([round(m.get(), 4) for m in metrics.values()])
+        out[f"{name}/ent_checksum"] = np.float64(ent.astype(np.float64).sum())
+        out[f"{name}/rel_checksum"] = np.float64(rel.astype(np.float64).sum())
+        for mi, mode in enumerate(("head-batch", "tail-batch")):
+            r64, cont = ko.rank_all(name, ent, rel, np.array(queries), mode, hc, tc, gamma=gamma,
+                                    rel_margins=CFG5_MARGINS)
+            out[f"{name}/{mode}/rank64"] = r64
+            out[f"{name}/{mode}/contested"] = cont  # [Q, len(CFG5_MARGINS)]
+            print(name, mode, "ref==fp64:", int((ranks[mi] == r64).sum()), "/", nq, "contested>0:",
+                  (cont > 0).sum(0).tolist(), "max |ref-fp64|", int(np.abs(ranks[mi] - r64).max()),
+                  "median rank", int(np.median(r64)), f"ref eval {t_ref:.0f}s", flush=True)
+    out["margins"] = np.array(CFG5_MARGINS)
+    np.savez_compressed(os.path.join(HERE, "cfg5_wn18rr.npz"), **out)
+    print("cfg5_wn18rr", len(out))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next", "distill", "distilldoc"]
+    if "cfg5" in which:  # ~20 min of CPU (the reference ranks 40 943 candidates x D=1000 per query)
+        gen_cfg5_cases(*[int(a) for a in which[which.index("cfg5") + 1:][:2]])
+        sys.exit(0)
     if "next" in which:
         gen_next_rows()
     if "distill" in which:
