@@ -330,6 +330,100 @@ def run_reference(args):
     return 0
 
 
+
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    return hbm, src
+
+
+def ncu_entry(cfg, role):
+    """Per-launch DRAM bytes and unit throughputs of this config's kernel from the committed ncu capture
+    (profiles/ncu_traffic.json, written by scripts/ncu_summary.py from an `ncu --set full` run of this bench)."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[cfg]
+        return tr[role], tr.get("source")
+    except Exception:
+        return None, None
+
+
+def kernel_roofline(cfg, role, name, algo_bytes, ms, hbm, peak_src):
+    """achieved = ALGORITHMIC bytes / CUDA-event time measured live (every gathered row counted once
+    per use, so rows served by the L2 count too and `frac` can exceed 1 for an L2-resident table); frac_dram =
+    the DRAM bytes ncu counted for one launch of this kernel / the same live time — the real HBM fraction; `bound`
+    is the unit ncu saw closest to its peak, not an assertion."""
+    ent, src = ncu_entry(cfg, role)
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    out = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+           "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ms,
+           "frac_logical": gbs / hbm, "frac_dram": None}
+    if ent:
+        traffic = int(ent["dram_read_bytes"] + ent["dram_write_bytes"])
+        lim = {"L1/TEX": "l1tex", "L2": "l2", "DRAM": "hbm", "SM": "sm"}.get(ent.get("limiter"), "hbm")
+        out.update({
+            "bound": lim, "traffic": traffic, "frac_dram": traffic / (ms * 1e-3) / 1e9 / hbm,
+            "limiter": {"unit": ent.get("limiter"), "l1tex_pct": ent.get("l1tex_pct"), "l2_pct": ent.get("l2_pct"),
+                        "dram_pct_of_nominal": ent.get("dram_pct"), "sm_pct": ent.get("sm_pct"),
+                        "l2_hit_pct": ent.get("l2_hit_pct"), "ncu_duration_us": ent.get("duration_us"),
+                        "source": f"profiles/ncu_traffic.json <- {src}"},
+        })
+        if lim != "hbm":
+            out["note"] = ("table is L2-resident at this config: the algorithmic (logical gather) bytes are mostly L2 hits, "
+                           "so frac > 1 is not an HBM fraction; frac_dram is.  See roofline_hbm_config for the config "
+                           "whose table exceeds the L2")
+    return out
+
+
+def hbm_config_run(dev, hbm, peak_src, cfg="cfg4", steps=40, warmup=5):
+    """A short device-resident run of config 4 (Yago3-10 shape, RotatE dim 500: entity table 493 MB >> L2) so that
+    the bench line carries one set of fractions that are true HBM fractions: per kernel, algorithmic bytes / live
+    CUDA-event time and ncu DRAM bytes / the same time, both against the measured copy bandwidth."""
+    from mkb_b200 import models, sampling
+    from mkb_b200.compose import DeviceTrainer
+    from mkb_b200.datasets.dataset import subsampling_weights
+
+    ds, mname, N, R, T, D, B, K, gamma = CONFIGS[cfg]
+    graph = synth_graph(cfg)
+    torch.manual_seed(42)
+    model = getattr(models, mname)(hidden_dim=D, entities={i: i for i in range(N)},
+                                   relations={i: i for i in range(R)}, gamma=gamma).to(dev)
+    ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R), seed=42, device=dev)
+    trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B)
+    w_all = subsampling_weights(graph)
+    order = np.random.RandomState(43).permutation(len(graph))[: (steps + warmup) * B].reshape(steps + warmup, B)
+    samples = torch.from_numpy(graph[order]).to(dev)
+    weights = w_all[torch.from_numpy(order)].to(dev)
+    modes = ["head-batch" if i % 2 == 0 else "tail-batch" for i in range(steps + warmup)]
+    for i in range(warmup):
+        trainer.step(samples[i], weights[i], modes[i])
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for i in range(steps):
+        trainer.hooks = ev[i]
+        trainer.step(samples[warmup + i], weights[warmup + i], modes[warmup + i])
+    t1.record()
+    torch.cuda.synchronize()
+    trainer.hooks = None
+    ms = t0.elapsed_time(t1) / steps
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    adam_ms = float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
+    fwd_b, bwd_b = algorithmic_bytes(cfg)
+    row_e, row_r = row_bytes(mname, D)
+    return {
+        "workload": workload_name(cfg), "steps": steps, "warmup": warmup, "ms_per_step": ms,
+        "value": B * (1 + K) / (ms * 1e-3), "unit": UNIT,
+        "fwd": kernel_roofline(cfg, "fwd", "score_neg_kernel<FUSED> (K2)", fwd_b, fwd_ms, hbm, peak_src),
+        "bwd": kernel_roofline(cfg, "bwd", "score_bwd_kernel (K3)", bwd_b, bwd_ms, hbm, peak_src),
+        "adam": kernel_roofline(cfg, "adam", "adam_kernel x2", 7 * (N * row_e + R * row_r), adam_ms, hbm, peak_src),
+    }
+
 # ------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------
@@ -395,7 +489,7 @@ def run_ours(args):
     for i in range(warmup):
         trainer.step(dev_samples[i], dev_weights[i], modes[i])
     ns.check_status(dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launches
     barrier()
@@ -411,6 +505,10 @@ def run_ours(args):
     ms_total = t0.elapsed_time(t1)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    try:  # the single-GPU flow also brackets the two Adam launches
+        adam_ms = float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
+    except Exception:
+        adam_ms = None
     final_loss = trainer.loss()
     ns.check_status(dev)
 
@@ -439,9 +537,9 @@ def run_ours(args):
     e2e_passes = []
     try:
         pipe.learn(model=model2, dataset=ds_warm, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
-        for _ in range(2):  # two full passes; the faster one is reported (a cold first pass has been seen
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)  # to pay
-            barrier()  # one-off driver/allocator costs), both are listed in e2e.passes_ms_per_step
+        for _ in range(3):  # three full passes over the same K-step dataset; the MEDIAN is reported, all are listed
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
             e0.record()
             pipe.learn(model=model2, dataset=ds_time, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
             e1.record()
@@ -451,17 +549,17 @@ def run_ours(args):
         if dist:
             raise  # a rank that leaves the collectives early would hang the others
         e2e_error = f"{type(e).__name__}: {e}"[:300]
-        e2e_passes = [float("nan"), float("nan")]
+        e2e_passes = [float("nan")] * 3
     finally:
         sys.stderr = _err
-    e2e_ms = min(e2e_passes) * steps  # per-step time of the faster pass x `steps`
+    e2e_ms = float(np.median(e2e_passes)) * steps  # per-step time of the median pass x `steps`
     e2e_loss = pipe.metric_loss.get()
 
     # ---------------- reduce over ranks ----------------
     e2e_passes_t = torch.tensor(e2e_passes, dtype=torch.float64, device=dev)
     if dist:
         torch.distributed.all_reduce(e2e_passes_t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms = float(e2e_passes_t.min().item()) * steps
+        e2e_ms = float(e2e_passes_t.median().item()) * steps  # median over passes of the max over ranks
     t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
     if dist:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -471,21 +569,17 @@ def run_ours(args):
     e2e_value = triples_per_step * steps / (e2e_ms * 1e-3)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        hbm, peak_src = load_peaks()
         fwd_b, bwd_b = algorithmic_bytes(cfg)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[cfg]["bwd_dram_bytes"]
-        except Exception:
-            pass
-        bwd_gbs = bwd_b / (bwd_ms * 1e-3) / 1e9
-        fwd_gbs = fwd_b / (fwd_ms * 1e-3) / 1e9
+        roof = kernel_roofline(cfg, "bwd", "score_bwd_kernel (fused backward, K3)" if trainer.backward == "scatter" else
+                               "by-entity backward incl. the entity table's Adam (byent.cu; bytes still counted as K3's)",
+                               bwd_b, bwd_ms, hbm, peak_src)
+        roof["share_of_step"] = bwd_ms / (ms_total / steps)
+        roof["also"] = kernel_roofline(cfg, "fwd", "score_neg_kernel<FUSED> (fused forward, K2)", fwd_b, fwd_ms, hbm, peak_src)
+        if adam_ms:
+            roof["adam"] = kernel_roofline(cfg, "adam", "adam_kernel x2 (dense Adam + gradient zeroing, both tables)",
+                                           7 * (N * row_bytes(mname, D)[0] + R * row_bytes(mname, D)[1]),
+                                           adam_ms, hbm, peak_src)
         row_e, row_r = row_bytes(mname, D)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -524,22 +618,14 @@ def run_ours(args):
                         "2 x adam_slice_bcast",
                 "final_loss": final_loss,
             },
-            "roofline": {
-                "kernel": "score_bwd_kernel (fused backward, K3)" if trainer.backward == "scatter" else
-                          "by-entity backward incl. the entity table's Adam (byent.cu; bytes still counted as K3's)",
-                "bound": "hbm", "achieved": bwd_gbs, "peak": hbm,
-                "unit": "GB/s", "frac": bwd_gbs / hbm, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bwd_b, "avg_launch_ms": bwd_ms,
-                "also": {"kernel": "score_neg_kernel<FUSED> (fused forward, K2)", "achieved": fwd_gbs,
-                         "frac": fwd_gbs / hbm, "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": fwd_ms},
-            },
+            "roofline": roof,
             "e2e": {"value": None if e2e_error else e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
                     "d2h_bytes_per_step": 16, "ms_per_step": None if e2e_error else e2e_ms / steps,
                     "api": "compose.Pipeline.learn(models.*, datasets.Dataset(host, pinned), sampling.NegativeSampling, "
                            "optim.DenseAdam, losses.Adversarial): per step H2D sample+weight, D2H loss sums",
                     "rolling_loss": e2e_loss, "passes_ms_per_step": None if e2e_error else e2e_passes_t.tolist(),
-                    "note": "faster of two timed passes of Pipeline.learn over the same K-step dataset",
+                    "note": "median of three timed passes of Pipeline.learn over the same K-step dataset",
                     **({"error": e2e_error} if e2e_error else {})},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -567,6 +653,12 @@ def run_ours(args):
                                          "e2e": None if e2e_error else e2e_value / r["value"]}}
             except Exception as e:
                 line["reference_on_this_gpu"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        if world == 1 and cfg != "cfg4" and not args.no_hbm_config:
+            try:  # the config whose table (493 MB) exceeds the 126 MB L2: the fractions there ARE HBM fractions
+                torch.cuda.empty_cache()
+                line["roofline_hbm_config"] = hbm_config_run(dev, hbm, peak_src)
+            except Exception as e:
+                line["roofline_hbm_config"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line))
     if dist:
         torch.distributed.barrier()
@@ -582,6 +674,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-config", action="store_true",
+                    help="skip the short config-4 run that adds roofline_hbm_config to the line")
     ap.add_argument("--cpu-budget", type=float, default=150.0,
                     help="--impl reference: seconds of CPU work the bounded sample is sized for (all steps together)")
     ap.add_argument("--mode", default=None, choices=["colpar", "allreduce", "rowshard"],

@@ -164,7 +164,7 @@ class DeviceTrainer:
         # every rank draws its own negatives: the same user seed, a rank-specific Philox key
         self._seed = (int(sampling.seed) + 0x9E3779B97F4A7C15 * self.rank) & (2 ** 64 - 1)
         self.t = 0
-        self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd] CUDA events (bench.py)
+        self.hooks = None  # optional [pre_fwd, post_fwd, pre_bwd, post_bwd(, pre_adam, post_adam)] CUDA events (bench.py)
 
         # single-GPU flow: "scatter" = K3 (vector REDs into a dense gradient) + dense Adam;
         # "by_entity" = csrc/byent.cu (per-step CSR by entity, no atomics, Adam fused, deterministic)
@@ -433,11 +433,15 @@ class DeviceTrainer:
             ops.adam_step(mod, self.g_mod, self.m_mod, self.v_mod, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
         if self.distributed:
             parallel.allreduce_gradients(self._gflat, self.group)
+        if h and len(h) > 5:
+            h[4].record()
         if self.backward != "by_entity":  # by_entity already applied Adam to both tables
             ops.adam_step(self.ent, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps,
                           zero_grad=True)
             ops.adam_step(self.rel, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps,
                           zero_grad=True)
+        if h and len(h) > 5:
+            h[5].record()
         return self.stats
 
     def _step_pooled(self, sample, weight, B, mode, h):
