@@ -460,7 +460,8 @@ def run_ours(args):
     ns = sampling.NegativeSampling(size=K, train_triples=graph, entities=range(N), relations=range(R),
                                    seed=42 + rank, device=dev, pool=args.pool)
     topts = {"mode": args.mode, "backward": args.backward, "pooled_gemm": args.pooled_gemm,
-             "packed_records": args.packed_records, "merged_backward": args.merged_backward}
+             "packed_records": args.packed_records, "merged_backward": args.merged_backward,
+             "handshake": args.handshake}
     if args.virtual_shards:
         topts = {"mode": "rowshard", "virtual_shards": args.virtual_shards}
     trainer = DeviceTrainer(model, ns, lr=5e-5, max_batch=B, distributed=dist, **topts)
@@ -595,7 +596,8 @@ def run_ours(args):
                     f"single GPU, entity table in {trainer.n_shards} block-cyclic row shards (all local)")
                 if not dist else (
                     f"dp{world}, replicated tables; batch-parallel forward, column-parallel backward over the "
-                    f"all-gathered global batch, fused Adam + all-gather through NVLink peer stores"
+                    f"global batch (step records exchanged by {'NVLink peer stores + flags, no NCCL on the step' if trainer.handshake == 'peer' else 'NCCL all-gather'}), "
+                    f"fused Adam + all-gather through NVLink peer stores"
                     if trainer.mode == "colpar" else
                     f"dp{world}, entity table row-sharded block-cyclically over the GPUs (1/{world} of table, gradient "
                     f"and Adam state each); remote rows gathered by P2P loads, row gradients added into the owner's "
@@ -614,8 +616,10 @@ def run_ours(args):
                         if trainer.mode in ("single", "allreduce") else
                         "sample_negatives + fused_fwd_sharded + fused_bwd_sharded + adam(own shard(s)) + adam(relation)"
                         if trainer.mode == "rowshard" else
-                        f"sample_negatives + fused_fwd + all-gather(step records) + {world} x fused_bwd_chunk + "
-                        "2 x adam_slice_bcast",
+                        (f"wait(slices) + sample_negatives + fused_fwd + peer_copy(record) + signal + wait(records) + "
+                         f"1 multi-record fused_bwd_chunk + 2 x adam_slice_bcast + signal" if trainer.handshake == "peer" else
+                         f"sample_negatives + fused_fwd + all-gather(step records) + {world} x fused_bwd_chunk + "
+                         "2 x adam_slice_bcast"),
                 "final_loss": final_loss,
             },
             "roofline": roof,
@@ -685,6 +689,9 @@ def main():
     ap.add_argument("--backward", default="scatter", choices=["scatter", "by_entity"],
                     help="single-GPU backward: scatter = K3 vector REDs + dense Adam (default, the measured path); "
                          "by_entity = atomics-free per-entity backward with Adam fused in (csrc/byent.cu)")
+    ap.add_argument("--handshake", default=None, choices=["peer", "nccl"],
+                    help="colpar only: peer = NVLink peer-memory flags + record push, no NCCL on the step (default); "
+                         "nccl = round 1's three collectives per step")
     ap.add_argument("--packed-records", action="store_true",
                     help="colpar only: loss sums ride in the all-gathered step records, ONE multi-record backward launch "
                          "(98 %% efficiency on 2 GPUs; its 4/8-GPU runs timed out in round 1 and await diagnosis)")

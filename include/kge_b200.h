@@ -352,6 +352,23 @@ int kge_adam_step_chunk(float* param, float* grad_chunk, float* exp_avg, float* 
                         int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
                         kge_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NVLink peer-memory handshakes of the multi-GPU step (csrc/peer.cu).  The reference has no multi-GPU
+ * path (single device, mkb/compose/pipeline.py:183-187); these replace the NCCL collectives a
+ * data-parallel wrapper around its loop would issue per step.  All pointer arrays are HOST arrays of
+ * n_peers (<= 16) DEVICE pointers into peer-mapped (symmetric) memory, index = rank.
+ *   kge_peer_copy   : src[0:bytes] -> dst_peers[r] + dst_offset_bytes for every r != self (16-byte units).
+ *   kge_peer_signal : flag_peers[r][slot] = value on every peer r (self included), released at system
+ *                     scope: everything launched before it on `stream` is visible to whoever sees the flag.
+ *   kge_peer_wait   : returns (on the stream) once flags[r] >= value for all r < n; gives up after
+ *                     timeout_ns and ORs bit (r & 15) into *status instead of hanging the device.
+ * ------------------------------------------------------------------------------------------- */
+int kge_peer_copy(const void* src, void* const* dst_peers, int32_t n_peers, int32_t self,
+                  int64_t dst_offset_bytes, int64_t bytes, kge_stream_t stream);
+int kge_peer_signal(void* const* flag_peers, int32_t n_peers, int32_t slot, uint32_t value, kge_stream_t stream);
+int kge_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, int64_t timeout_ns, int32_t* status,
+                  kge_stream_t stream);
+
 /* Column-parallel multi-GPU step (fused update + all-gather over NVLink peer memory): this rank owns
  * columns [col0, col0+ncols) of every row.  grad_slice / exp_avg_slice / exp_avg_sq_slice are dense
  * [rows, comps*ncols] slice buffers; param_replicas is a HOST array of n_replicas (<= 16) DEVICE

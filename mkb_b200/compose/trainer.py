@@ -37,12 +37,14 @@ positives).  Two schemes:
 In all of them, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
 global batch): the three loss sums are all-reduced between forward and backward.
 
-``packed_records=True`` (colpar only, opt-in) drops that all-reduce — the sums ride inside the
-all-gathered step records and the backward kernel adds them up — and runs the backward over all G
-records in ONE multi-record launch.  Measured on 2 GPUs: 0.777 vs 0.832 ms/step, parity-tested.  It is
-NOT the default because a 4- and an 8-GPU bench run with it hit their time limit in the last GPU call
-of round 1 and could not be diagnosed before the GPU budget ran out; the default flow below was
-measured on 2, 4 and 8 GPUs.
+``handshake="peer"`` (colpar default since round 2) — NO NCCL call on the step.  The step records live in
+symmetric memory; after its forward a rank pushes its record into every peer (`kge_peer_copy`, NVLink
+stores) and raises flag[phase 0][rank] = step there (`kge_peer_signal`); a one-warp wait kernel holds the
+stream until all G flags show the step (`kge_peer_wait`); ONE multi-record backward launch covers the global
+batch with the loss sums read from the records (no all-reduce); after the fused Adam + all-gather
+(`kge_adam_slice_bcast`) flag[phase 1][rank] = step is raised everywhere and the NEXT forward waits for all G
+of those.  Round 1 spent ~0.1 ms per step (more at 8 GPUs) in three latency-bound NCCL collectives instead.
+``handshake="nccl"`` keeps that flow (and its ``packed_records`` / ``merged_backward`` variants) for A/B runs.
 """
 from __future__ import annotations
 
@@ -102,7 +104,7 @@ class DeviceTrainer:
 
     def __init__(self, model, sampling, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, alpha=0.5, max_batch=1024,
                  process_group=None, distributed=False, mode=None, packed_records=False, virtual_shards=None,
-                 scalar_red=False, backward="scatter", pooled_gemm=False, merged_backward=False):
+                 scalar_red=False, backward="scatter", pooled_gemm=False, merged_backward=False, handshake=None):
         ent, rel = model.entity_embedding, model.relation_embedding
         if not ent.is_cuda:
             raise ops.N.KgeError("DeviceTrainer needs the model on a CUDA device")
@@ -139,6 +141,12 @@ class DeviceTrainer:
                 self.mode_note = f"colpar unavailable ({type(e).__name__}: {e}); using allreduce"
                 mode = "allreduce"
         self.mode = mode
+        if handshake not in (None, "peer", "nccl"):
+            raise ValueError("handshake must be 'peer' or 'nccl'")
+        # peer-memory flags instead of NCCL collectives (colpar only); the nccl variants stay for A/B runs
+        self.handshake = (handshake or ("nccl" if (packed_records or merged_backward) else "peer")) if mode == "colpar" else None
+        if self.handshake == "peer":
+            packed_records = True  # the loss sums ride in the records
         # colpar, opt-in: ONE backward launch over all G gathered records (global stats from the all-reduce)
         # instead of one launch per source rank; keeps the collectives of the measured default flow
         self.merged_backward = bool(merged_backward) and mode == "colpar"
@@ -241,7 +249,29 @@ class DeviceTrainer:
         o_stats = (o_cneg + B * K * 4 + 15) // 16 * 16
         rec = o_stats + (16 if self.packed_records else 0)
         self._rec_stride = rec
-        self._rec_all = torch.zeros(G * rec, dtype=torch.uint8, device=self.dev)
+        if self.handshake == "peer":
+            # records + two flag arrays (phase 0: "record of step t is here", phase 1: "table slice of step t is
+            # here"; 16 uint32 each) in ONE symmetric allocation, so peers can store into both
+            import torch.distributed._symmetric_memory as symm
+
+            group = self.group if self.group is not None else torch.distributed.group.WORLD
+            buf = symm.empty(G * rec + 128, dtype=torch.uint8, device=self.dev)
+            buf.zero_()
+            torch.cuda.synchronize(self.dev)
+            hdl = symm.rendezvous(buf, group)
+            self._symm.append(hdl)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != G or ptrs[self.rank] != buf.data_ptr():
+                raise RuntimeError("unexpected symmetric-memory pointer table")
+            self._rec_ptrs = ptrs
+            self._flag_ptrs = [[p + G * rec + 64 * ph for p in ptrs] for ph in (0, 1)]
+            self._flags = [buf[G * rec + 64 * ph: G * rec + 64 * ph + 64].view(torch.int32) for ph in (0, 1)]
+            self._peer_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._rec_all = buf[: G * rec]
+            torch.cuda.synchronize(self.dev)
+            torch.distributed.barrier(group=self.group)  # every rank's flags are zero before anyone signals
+        else:
+            self._rec_all = torch.zeros(G * rec, dtype=torch.uint8, device=self.dev)
         self._recs = []
         for r in range(G):
             base = self._rec_all[r * rec:(r + 1) * rec]
@@ -310,6 +340,7 @@ class DeviceTrainer:
     def sync_model(self):
         """Write the trained shards back into ``model.entity_embedding`` (all-gather in the distributed
         case) so evaluation / save / the user's own code see the current table."""
+        self.flush()
         if self.mode != "rowshard":
             return
         full = self.model.entity_embedding.data
@@ -398,6 +429,9 @@ class DeviceTrainer:
         h = self.hooks
         if self.mode == "rowshard":
             return self._step_rowshard(sample, weight, B, mode, h)
+        if self.handshake == "peer":
+            # every peer's column slice of the previous step has landed in this replica
+            ops.peer_wait(self._flags[1], self.world, self.t, self._peer_status)
         if h:
             h[0].record()
         packed = self.packed_records
@@ -467,7 +501,13 @@ class DeviceTrainer:
         # Together with the loss-sum all-reduce before it, it is the "every rank finished its forward"
         # point after which table columns may be overwritten by their owners.
         self._recs[self.rank][0][:B].copy_(sample)
-        torch.distributed.all_gather_into_tensor(self._rec_all, self._rec_local, group=self.group)
+        peer = self.handshake == "peer"
+        if peer:
+            ops.peer_copy(self._rec_local, self._rec_ptrs, self.rank, self.rank * self._rec_stride)
+            ops.peer_signal(self._flag_ptrs[0], self.rank, self.t, self.dev)  # "my forward is done, my record is there"
+            ops.peer_wait(self._flags[0], self.world, self.t, self._peer_status)
+        else:
+            torch.distributed.all_gather_into_tensor(self._rec_all, self._rec_local, group=self.group)
         if h:
             h[2].record()
         if self.ncols > 0 and self.packed_records:
@@ -494,11 +534,25 @@ class DeviceTrainer:
                 ops.adam_slice_bcast(reps, self.rank, g, m, v, tbl.shape[0], comps, self.ncols, self.col0,
                                      tbl.shape[1], self.D, self.t, self.lr, b1, b2, self.eps, device=self.dev)
         # every replica must hold every slice before anyone's next forward reads the tables
-        torch.distributed.all_reduce(self._tiny, group=self.group)
+        if peer:
+            ops.peer_signal(self._flag_ptrs[1], self.rank, self.t, self.dev)  # waited for at the next step's start
+        else:
+            torch.distributed.all_reduce(self._tiny, group=self.group)
         if self.packed_records:
             torch.sum(self._stats_all, dim=0, out=self.stats)  # global (S_p, S_n, W, -) for loss()/logging
         return self.stats
 
+    def flush(self):
+        """colpar/peer: hold the stream until every peer's slice of the LAST step is in this replica (the next
+        step would do it; callers that read the tables — evaluation, save — need it now), then check that no
+        handshake timed out (synchronises)."""
+        if self.handshake == "peer":
+            ops.peer_wait(self._flags[1], self.world, self.t, self._peer_status)
+            bad = int(self._peer_status.item())
+            if bad:
+                raise RuntimeError(f"multi-GPU handshake timed out waiting for rank bit mask {bad:#x}")
+
     def loss(self):
         """Global loss of the last step (host float; synchronises)."""
+        self.flush()
         return float(parallel.loss_from_sums(self.stats).item())

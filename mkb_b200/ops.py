@@ -445,6 +445,34 @@ def adam_slice_bcast(replica_ptrs, self_index, grad_slice, m_slice, v_slice, row
     N.count_launch()
 
 
+def peer_copy(src, dst_ptrs, self_index, dst_offset_bytes, nbytes=None):
+    """``src`` (contiguous device tensor) -> every peer's buffer at ``dst_offset_bytes`` (NVLink stores)."""
+    lib = N.load()
+    nbytes = src.numel() * src.element_size() if nbytes is None else int(nbytes)
+    arr = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    N.check(lib.kge_peer_copy(N.ptr(src), arr, len(dst_ptrs), self_index, int(dst_offset_bytes), nbytes,
+                              N.stream_ptr(src.device)), "kge_peer_copy")
+    if len(dst_ptrs) > 1 and nbytes:
+        N.count_launch()
+
+
+def peer_signal(flag_ptrs, slot, value, device):
+    """flags[r][slot] = value on every peer r, released at system scope after all prior work of the stream."""
+    lib = N.load()
+    arr = (C.c_void_p * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
+    N.check(lib.kge_peer_signal(arr, len(flag_ptrs), int(slot), int(value) & 0xFFFFFFFF, N.stream_ptr(device)),
+            "kge_peer_signal")
+    N.count_launch()
+
+
+def peer_wait(flags, n, value, status, timeout_s=20.0):
+    """Blocks the STREAM (not the host) until flags[0:n] >= value; a time-out raises ``status`` instead of hanging."""
+    lib = N.load()
+    N.check(lib.kge_peer_wait(N.ptr(flags), int(n), int(value) & 0xFFFFFFFF, int(timeout_s * 1e9), N.ptr(status),
+                              N.stream_ptr(flags.device)), "kge_peer_wait")
+    N.count_launch()
+
+
 # ---------------------------------------------------------------------------------------------
 # K7: row-sharded entity table (block-cyclic: entity e -> shard e % G, local row e / G)
 # ---------------------------------------------------------------------------------------------

@@ -49,6 +49,7 @@ class Args:
 
 Args.backward, Args.virtual_shards, Args.pool, Args.pooled_gemm = backward, int(vshards), pool, gemm == "1"
 Args.packed_records = Args.merged_backward = False
+Args.handshake = None
 Args.no_hbm_config = os.environ.get("DRYRUN_HBM_CONFIG") != "1"  # the config-4 leg is too big for the emulation
 bench.reference_run = lambda *a, **k: None
 sys.exit(bench.run_ours(Args))

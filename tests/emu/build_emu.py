@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "mkb_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libkge_emu.so")
-SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu", "byent.cu", "pooled.cu"]
+SOURCES = ["api.cu", "loss.cu", "sampler.cu", "score.cu", "rank.cu", "topk.cu", "byent.cu", "pooled.cu", "peer.cu"]
 HEADERS = ["kge_common.cuh"]
 
 
@@ -163,6 +163,9 @@ def rewrite_asm(text):
             code = f"{outs[0]} = sqrtf({ins[0]});"
         elif ptx.startswith("rsqrt.approx"):
             code = f"{outs[0]} = 1.0f / sqrtf({ins[0]});"
+        elif "globaltimer" in ptx:  # nanosecond wall clock
+            code = (f"{{ struct timespec _ts; clock_gettime(CLOCK_MONOTONIC, &_ts); "
+                    f"{outs[0]} = (long long)_ts.tv_sec * 1000000000LL + _ts.tv_nsec; }}")
         else:
             raise ValueError(f"no emulation for PTX statement: {ptx}")
         out.append(text[pos:m.start()])

@@ -13,6 +13,7 @@
 // launches, `extern __shared__` arrays and the inline-PTX statements — and compiles with this file
 // standing in for <cuda_runtime.h>.
 #pragma once
+#include <time.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -385,6 +386,7 @@ inline void __syncthreads(int line = __builtin_LINE()) {
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 template <class T>
 inline T __shfl_sync(unsigned mask, T v, int src, int line = __builtin_LINE()) {
   return emu::warp_exchange(v, src, mask, line);

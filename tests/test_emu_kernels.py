@@ -733,3 +733,34 @@ def test_pooled_adv_kernel_in_the_opt_in_shared_memory_window():
     _close(ps, f["pos"].astype(np.float64), 1e-5)
     _close(ns, f["neg"].astype(np.float64), 1e-5)
     np.testing.assert_allclose(stats, f["stats"], rtol=1e-5)
+
+
+def test_peer_handshake_primitives():
+    """kge_peer_copy / kge_peer_signal / kge_peer_wait (csrc/peer.cu) with three "peers" that are local buffers:
+    a record pushed by rank 1 lands in every other peer at its offset and nowhere else, flags are raised on every
+    peer, a satisfied wait returns with a clean status and an unsatisfied one times out instead of hanging."""
+    l = H.lib()
+    G, rec = 3, 64
+    bufs = [np.zeros(G * rec + 128, np.uint8) for _ in range(G)]
+    src = np.arange(rec, dtype=np.uint8) + 1
+    arr = (C.c_void_p * G)(*[H.P(b) for b in bufs])
+    H.ok(l.kge_peer_copy(H.P(src), arr, G, 1, 1 * rec, rec, None))
+    for r in range(G):
+        got = bufs[r][rec:2 * rec]
+        assert np.array_equal(got, src) == (r != 1)  # the sender's own slot is written by its forward, not the copy
+        assert not bufs[r][:rec].any() and not bufs[r][2 * rec:].any()
+    flags = (C.c_void_p * G)(*[H.P(b) + G * rec for b in bufs])
+    status = np.zeros(1, np.int32)
+    for rank in range(G):
+        H.ok(l.kge_peer_signal(flags, G, rank, 7, None))
+    for r in range(G):
+        f = bufs[r][G * rec:G * rec + 64].view(np.uint32)
+        assert f[:G].tolist() == [7] * G and not f[G:].any()
+        H.ok(l.kge_peer_wait(H.P(bufs[r]) + G * rec, G, 7, int(1e9), H.P(status), None))
+        H.ok(l.kge_peer_wait(H.P(bufs[r]) + G * rec, G, 5, int(1e9), H.P(status), None))  # a later waiter: >=
+    assert status[0] == 0
+    bufs[0][G * rec + 4:G * rec + 8].view(np.uint32)[0] = 6  # rank 1 never reached step 7 on peer 0
+    H.ok(l.kge_peer_wait(H.P(bufs[0]) + G * rec, G, 7, int(2e7), H.P(status), None))
+    assert status[0] == 1 << 1
+    assert l.kge_peer_copy(H.P(src), arr, G, 1, 8, rec, None) == -5
+    assert l.kge_peer_wait(None, G, 1, 1, H.P(status), None) == -1

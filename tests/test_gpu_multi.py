@@ -72,7 +72,7 @@ def test_two_gpu_step_matches_single_gpu_global_batch():
     assert out["ent_err"] < 1e-5 and out["rel_err"] < 1e-5
 
 
-def _worker_trainer(rank, world, port, out, mode, packed=False):
+def _worker_trainer(rank, world, port, out, mode, packed=False, handshake=None):
     """DeviceTrainer in a multi-GPU mode vs rank 0 replaying the GLOBAL batch on one GPU."""
     import torch.distributed as dist
 
@@ -93,7 +93,8 @@ def _worker_trainer(rank, world, port, out, mode, packed=False):
     torch.manual_seed(1)
     ref = models.RotatE(hidden_dim=D, entities=ents, relations=rels, gamma=9.0).to(dev)
     ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=5 + rank)
-    tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, distributed=True, mode=mode, packed_records=packed)
+    tr = DeviceTrainer(m, ns, lr=1e-3, max_batch=B, distributed=True, mode=mode, packed_records=packed,
+                       handshake=handshake)
     opt = optim.DenseAdam([ref.entity_embedding, ref.relation_embedding], lr=1e-3)
     errs = []
     for step in range(4):
@@ -122,22 +123,25 @@ def _worker_trainer(rank, world, port, out, mode, packed=False):
     if rank == 0:
         out["ent"], out["rel"], out["loss"] = res.tolist()
         out["mode"], out["note"], out["moved"] = tr.mode, tr.mode_note, moved
+        out["handshake"] = tr.handshake
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode,packed", (("colpar", False), ("colpar", True), ("allreduce", False)))
-def test_two_gpu_trainer_matches_single_gpu(mode, packed):
+@pytest.mark.parametrize("mode,packed,handshake", (("colpar", False, "peer"), ("colpar", False, "nccl"),
+                                                   ("colpar", True, "nccl"), ("allreduce", False, None)))
+def test_two_gpu_trainer_matches_single_gpu(mode, packed, handshake):
     import torch.multiprocessing as mp
 
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     out = mp.Manager().dict()
-    mp.spawn(_worker_trainer, args=(2, port, out, mode, packed), nprocs=2, join=True)
+    mp.spawn(_worker_trainer, args=(2, port, out, mode, packed, handshake), nprocs=2, join=True)
     print(dict(out))
     assert out["mode"] == mode, out["note"]
+    assert out["handshake"] == handshake
     assert out["loss"] < 1e-5
     # 4 Adam steps of lr 1e-3 move parameters by ~4e-3; replicas must agree with the replay to ~1e-6
     assert out["ent"] < 2e-5 and out["rel"] < 2e-5

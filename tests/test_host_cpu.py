@@ -575,3 +575,28 @@ def test_graft_entry_smoke_on_the_emulation():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "smoke_dryrun.py")], capture_output=True,
                        text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_pipeline_rank_slices_partition_the_global_batch():
+    """compose.Pipeline._rank_slice (multi-rank learn): the ranks' blocks cover every row of the dataset's batch
+    exactly once; short blocks are padded with weight-0 rows so that every rank keeps the same local batch size."""
+    import types
+
+    import torch
+
+    from mkb_b200.compose import Pipeline
+
+    for B, world in ((12, 4), (10, 4), (3, 4), (7, 2), (1024, 8), (5, 1)):
+        sample = torch.arange(B * 3).view(B, 3)
+        weight = torch.arange(1, B + 1, dtype=torch.float32)
+        per = -(-B // world)
+        seen, wsum = [], 0.0
+        for rank in range(world):
+            s, w = Pipeline._rank_slice(sample, weight, types.SimpleNamespace(world=world, rank=rank))
+            assert s.shape == (per, 3) and w.shape == (per,) and s.is_contiguous()
+            real = w > 0
+            seen += s[real][:, 0].tolist()
+            wsum += float(w.sum())
+            assert torch.equal(s[~real], sample[:1].expand(int((~real).sum()), 3))  # padding = row 0 at weight 0
+        assert sorted(seen) == sample[:, 0].tolist()
+        assert wsum == float(weight.sum())
