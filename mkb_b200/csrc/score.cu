@@ -268,6 +268,10 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
   }
 }
 
+}  // namespace kge
+#include "score_tma.cuh"  // K2-TMA: the same fused forward with rows staged through cp.async.bulk
+namespace kge {
+
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -908,6 +912,61 @@ extern "C" size_t kge_loss_workspace_bytes(int64_t B) {
   return (size_t)(3 * (B > 0 ? B : 0)) * sizeof(float) + 16;
 }
 
+// K2-TMA launcher (score_tma.cuh).  Returns KGE_E_UNSUPPORTED when the shape does not fit the variant
+// (the caller then uses the LDG kernel).
+template <int M, bool HEAD, int UMAX, int MINB>
+static int launch_neg_tma(const FwdParams& p, int stages, size_t smem, int grid, int* fail, cudaStream_t st) {
+  auto kern = score_neg_tma_kernel<M, HEAD, UMAX, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, kThreads, smem, st>>>(p, stages, fail);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+static int run_fwd_tma(const kge_tables_t* t, int mode, const FwdParams& p, int* fail, cudaStream_t st) {
+  const int D = t->hidden_dim;
+  if (!can_vectorize(t) || D > 1024 || t->model == KGE_PROTATE) return KGE_E_UNSUPPORTED;
+  const int minb = env_int("KGE_TMA_MINB", 1) >= 2 ? 2 : 1;
+  const size_t row_bytes = (size_t)p.ent_stride * 4;
+  const size_t Kp = ((size_t)p.K + 3) & ~(size_t)3;
+  const size_t fixed = ((size_t)entity_comps(t->model) * p.Dp + 2 * Kp) * 4;
+  const size_t budget = (size_t)(minb == 1 ? 220 : 108) * 1024;
+  if (fixed + 64 + kWarps * row_bytes > budget) return KGE_E_UNSUPPORTED;
+  int stages = (int)((budget - fixed) / (kWarps * row_bytes + 64));
+  if (stages > 8) stages = 8;
+  const int want = env_int("KGE_TMA_STAGES", 0);
+  if (want > 0 && want < stages) stages = want;
+  if (stages < 1) return KGE_E_UNSUPPORTED;
+  const size_t smem = fixed + (size_t)stages * (kWarps * row_bytes + 64);
+  int grid = sm_count() * minb;
+  if (grid > p.B) grid = p.B;
+  const int umax = D <= 256 ? 2 : (D <= 512 ? 4 : 8);
+#define KGE_TMA_CASE3(MM, HH, UU)                                                                      \
+  return minb == 2 ? launch_neg_tma<MM, HH, UU, 2>(p, stages, smem, grid, fail, st)                    \
+                   : launch_neg_tma<MM, HH, UU, 1>(p, stages, smem, grid, fail, st);
+#define KGE_TMA_CASE2(MM, HH)                                                                          \
+  if (umax == 2) { KGE_TMA_CASE3(MM, HH, 2) } else if (umax == 4) { KGE_TMA_CASE3(MM, HH, 4) } else { KGE_TMA_CASE3(MM, HH, 8) }
+#define KGE_TMA_CASE(MM)                                                                               \
+  case MM:                                                                                             \
+    if (mode == KGE_HEAD_BATCH) { KGE_TMA_CASE2(MM, true) } else { KGE_TMA_CASE2(MM, false) }
+  switch (t->model) {
+    KGE_TMA_CASE(KGE_TRANSE)
+    KGE_TMA_CASE(KGE_DISTMULT)
+    KGE_TMA_CASE(KGE_COMPLEX)
+    KGE_TMA_CASE(KGE_ROTATE)
+  }
+#undef KGE_TMA_CASE
+#undef KGE_TMA_CASE2
+#undef KGE_TMA_CASE3
+  return KGE_E_MODEL;
+}
+
 extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
                              const int64_t* neg, int64_t K, const float* weight, float alpha,
                              float* pos_score, float* neg_score, float* coef_pos, float* coef_neg,
@@ -933,6 +992,10 @@ extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sam
   p.K = (int)K;
   p.k_per_cta = (int)K;
   p.alpha = alpha;
+  if (env_int("KGE_FWD_TMA", 0)) {  // A/B switch: rows staged through the TMA (score_tma.cuh)
+    rc = run_fwd_tma(t, mode, p, reinterpret_cast<int*>(workspace) + 1, (cudaStream_t)stream);
+    if (rc != KGE_E_UNSUPPORTED) return rc;
+  }
   const size_t smem = ((size_t)entity_comps(t->model) * p.Dp + (size_t)K) * sizeof(float);
   if (smem > 200 * 1024) return KGE_E_UNSUPPORTED;
   return dispatch_neg<true>(t->model, mode, can_vectorize(t), p, dim3((unsigned)B, 1), smem,
