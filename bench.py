@@ -474,7 +474,8 @@ def run_ours(args):
     n_batches = steps + warmup
     need = n_batches * B * world
     reps = -(-need // len(perm))
-    order = np.tile(perm, reps)[:need].reshape(n_batches, world, B)[:, rank, :]
+    order_all = np.tile(perm, reps)[:need].reshape(n_batches, world, B)  # global batch g = order_all[g]
+    order = order_all[:, rank, :]
     host_samples = torch.from_numpy(graph[order]).pin_memory()  # [n_batches, B, 3]
     host_weights = weights_all[torch.from_numpy(order)].pin_memory()
     dev_samples = host_samples.to(dev)
@@ -524,13 +525,14 @@ def run_ours(args):
     opt = optim.DenseAdam(filter(lambda p: p.requires_grad, model2.parameters()), lr=5e-5)
     ents, rels = {i: i for i in range(N)}, {i: i for i in range(R)}
 
-    def host_dataset(rows):  # an epoch of Dataset = one head-batch + one tail-batch per B triples
-        return datasets.Dataset(train=rows, entities=ents, relations=rels, batch_size=B, shuffle=False,
-                                seed=None, pin_memory=True)
+    def host_dataset(batches):  # an epoch of Dataset = one head-batch + one tail-batch per GLOBAL batch of B * world
+        # triples; under torch.distributed Pipeline.learn gives rank r the r-th block of B rows of every batch
+        return datasets.Dataset(train=graph[batches.reshape(-1)], entities=ents, relations=rels, batch_size=B * world,
+                                shuffle=False, seed=None, pin_memory=True)
 
     half = (steps + 1) // 2
-    ds_warm = host_dataset(graph[order[: max(warmup // 2, 2)].reshape(-1)])
-    ds_time = host_dataset(graph[order[warmup: warmup + half].reshape(-1)])
+    ds_warm = host_dataset(order_all[: max(warmup // 2, 2)])
+    ds_time = host_dataset(order_all[warmup: warmup + half])
     e2e_steps = 2 * half
     pipe = compose.Pipeline(epochs=1, device=dev, trainer_options=topts)
     sys.stderr, _err = open(os.devnull, "w"), sys.stderr  # tqdm's bar
@@ -624,7 +626,7 @@ def run_ours(args):
             },
             "roofline": roof,
             "e2e": {"value": None if e2e_error else e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(B * 3 * 8 + B * 4),
+                    "h2d_bytes_per_step": int(B * 3 * 8 + B * 4) * world,
                     "d2h_bytes_per_step": 16, "ms_per_step": None if e2e_error else e2e_ms / steps,
                     "api": "compose.Pipeline.learn(models.*, datasets.Dataset(host, pinned), sampling.NegativeSampling, "
                            "optim.DenseAdam, losses.Adversarial): per step H2D sample+weight, D2H loss sums",

@@ -10,6 +10,7 @@ fi
 nvidia-smi topo -m > $OUT/topo_${N}gpu.txt 2>&1
 for cfg in cfg2 cfg4; do
   for hs in peer nccl; do
+    if [ "$N" -ge 4 ] && [ $cfg = cfg4 ] && [ $hs = nccl ]; then continue; fi
     timeout 300 $RUN bench.py --gpus $N --config $cfg --steps 100 --warmup 10 --mode colpar --handshake $hs \
         > $OUT/bench_${cfg}_${N}gpu_colpar_${hs}.json 2> $OUT/bench_${cfg}_${N}gpu_colpar_${hs}.err
   done
