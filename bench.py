@@ -495,6 +495,10 @@ def run_ours(args):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _native.launches
     barrier()
+    if dist:
+        # the host-side barrier leaves the ranks up to a few ms apart; a collective enqueued right before t0 lines
+        # the DEVICE timelines up, so the timed region holds K steps and not the slowest host's start-up skew
+        torch.distributed.all_reduce(torch.zeros(1, device=dev))
     with ClockSampler(local) as clocks:
         t0.record()
         for i in range(steps):
@@ -543,6 +547,8 @@ def run_ours(args):
         for _ in range(3):  # three full passes over the same K-step dataset; the MEDIAN is reported, all are listed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
+            if dist:
+                torch.distributed.all_reduce(torch.zeros(1, device=dev))
             e0.record()
             pipe.learn(model=model2, dataset=ds_time, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
             e1.record()

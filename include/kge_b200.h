@@ -352,6 +352,11 @@ int kge_adam_step_chunk(float* param, float* grad_chunk, float* exp_avg, float* 
                         int64_t step, float lr, float beta1, float beta2, float eps, int zero_grad,
                         kge_stream_t stream);
 
+/* Debug aid for the TMA-staged variants of K2 / K3 (csrc/score_tma.cuh, selected with KGE_FWD_TMA=1 /
+ * KGE_BWD_TMA=1): their mbarrier waits are bounded so that a copy that never completes cannot hang the device;
+ * this returns (and clears) a non-zero value if any wait gave up since the last call.  Synchronises. */
+int kge_tma_fail_flag(void);
+
 /* ---------------------------------------------------------------------------------------------
  * NVLink peer-memory handshakes of the multi-GPU step (csrc/peer.cu).  The reference has no multi-GPU
  * path (single device, mkb/compose/pipeline.py:183-187); these replace the NCCL collectives a

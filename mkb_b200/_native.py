@@ -86,6 +86,7 @@ PROTOTYPES = {
     "kge_adam_slice_bcast": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P, _I64, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I64, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_int, _P]),
+    "kge_tma_fail_flag": (C.c_int, []),
     "kge_peer_copy": (C.c_int, [_P, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _I64, _I64, _P]),
     "kge_peer_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, _P]),
     "kge_peer_wait": (C.c_int, [_P, C.c_int32, C.c_uint32, _I64, _P, _P]),

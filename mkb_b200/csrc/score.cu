@@ -268,10 +268,6 @@ __global__ void __launch_bounds__(kThreads, KGE_FWD_MINB) score_neg_kernel(FwdPa
   }
 }
 
-}  // namespace kge
-#include "score_tma.cuh"  // K2-TMA: the same fused forward with rows staged through cp.async.bulk
-namespace kge {
-
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
@@ -557,6 +553,10 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   }
 }
 
+}  // namespace kge
+#include "score_tma.cuh"  // K2-TMA / K3-TMA: the fused forward and backward with rows staged through the TMA
+namespace kge {
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -580,6 +580,11 @@ static int sm_count() {
   int dev = 0, n = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n > 0 ? n : 148;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
 }
 
 template <typename Kern>
@@ -684,6 +689,52 @@ static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t s
   return KGE_OK;
 }
 
+// K3-TMA launcher (score_tma.cuh): KGE_E_UNSUPPORTED when the shape does not fit (caller uses the scatter kernel).
+template <int M, bool HEAD, int UMAX>
+static int launch_bwd_tma(const BwdParams& p, int stages, int n_slices, size_t smem, int grid, cudaStream_t st) {
+  auto kern = score_bwd_tma_kernel<M, HEAD, UMAX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, kThreads, smem, st>>>(p, stages, n_slices, nullptr);
+  KGE_LAUNCH_CHECK();
+  return KGE_OK;
+}
+
+static int run_bwd_tma(const kge_tables_t* t, int mode, const BwdParams& p, int n_slices, cudaStream_t st) {
+  const int D = t->hidden_dim;
+  if (D > 1024 || D % 4 || t->model == KGE_PROTATE) return KGE_E_UNSUPPORTED;
+  const size_t row_bytes = (size_t)p.ent_stride * 4;
+  const size_t Kc = ((size_t)p.k_per_cta + 3) & ~(size_t)3;
+  const size_t fixed = ((size_t)entity_comps(t->model) * ((D + 3) & ~3) + 2 * Kc) * 4 + kWarps * row_bytes;
+  const size_t budget = 220 * 1024;
+  if (fixed + kWarps * row_bytes + 64 > budget) return KGE_E_UNSUPPORTED;
+  int stages = (int)((budget - fixed) / (kWarps * row_bytes + 64));
+  if (stages > 8) stages = 8;
+  const int want = env_int("KGE_TMA_STAGES", 0);
+  if (want > 0 && want < stages) stages = want;
+  const size_t smem = fixed + (size_t)stages * (kWarps * row_bytes + 64);
+  int64_t items = (int64_t)p.B * n_slices;
+  int grid = sm_count();
+  if (grid > items) grid = (int)items;
+  const int umax = D <= 256 ? 2 : (D <= 512 ? 4 : 8);
+#define KGE_TMA_CASE2(MM, HH)                                                                                  \
+  return umax == 2 ? launch_bwd_tma<MM, HH, 2>(p, stages, n_slices, smem, grid, st)                            \
+                   : (umax == 4 ? launch_bwd_tma<MM, HH, 4>(p, stages, n_slices, smem, grid, st)               \
+                                : launch_bwd_tma<MM, HH, 8>(p, stages, n_slices, smem, grid, st));
+#define KGE_TMA_CASE(MM)                                                                                       \
+  case MM:                                                                                                     \
+    if (mode == KGE_HEAD_BATCH) { KGE_TMA_CASE2(MM, true) } else { KGE_TMA_CASE2(MM, false) }
+  switch (t->model) {
+    KGE_TMA_CASE(KGE_TRANSE)
+    KGE_TMA_CASE(KGE_DISTMULT)
+    KGE_TMA_CASE(KGE_COMPLEX)
+    KGE_TMA_CASE(KGE_ROTATE)
+  }
+#undef KGE_TMA_CASE
+#undef KGE_TMA_CASE2
+  return KGE_E_MODEL;
+}
+
 // col0 / ncols select a column chunk of the hidden dim; ncols <= 0 means the whole row, in which case
 // the gradient buffers have the tables' own layout.  With a chunk, grad_ent / grad_rel are dense
 // [n_entity, NC*ncols] / [n_relation, RC*ncols] buffers holding just that chunk.
@@ -765,6 +816,10 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   if (gh_buf) ks = 1;  // pass 1 of the by-entity backward keeps a positive's whole dq in one CTA
   p.k_per_cta = p.K > 0 ? (p.K + ks - 1) / ks : 0;
   if (p.K > 0) ks = (p.K + p.k_per_cta - 1) / p.k_per_cta;
+  if (!sh && !chunked && n_records <= 1 && !gh_buf && vec && neg && gneg && env_int("KGE_BWD_TMA", 0)) {
+    const int rc_tma = run_bwd_tma(t, mode, p, ks, st);  // A/B switch: rows in AND gradients out through the TMA
+    if (rc_tma != KGE_E_UNSUPPORTED) return rc_tma;
+  }
   dim3 grid((unsigned)total, (unsigned)ks);
   const size_t smem = (size_t)(G - 1) * entity_comps(t->model) * tpg * VEC * sizeof(float);
   if (gh_buf) {
@@ -924,11 +979,6 @@ static int launch_neg_tma(const FwdParams& p, int stages, size_t smem, int grid,
   return KGE_OK;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
-
 static int run_fwd_tma(const kge_tables_t* t, int mode, const FwdParams& p, int* fail, cudaStream_t st) {
   const int D = t->hidden_dim;
   if (!can_vectorize(t) || D > 1024 || t->model == KGE_PROTATE) return KGE_E_UNSUPPORTED;
@@ -1000,6 +1050,13 @@ extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sam
   if (smem > 200 * 1024) return KGE_E_UNSUPPORTED;
   return dispatch_neg<true>(t->model, mode, can_vectorize(t), p, dim3((unsigned)B, 1), smem,
                             (cudaStream_t)stream);
+}
+
+extern "C" int kge_tma_fail_flag(void) {
+  int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, g_tma_fail, sizeof(int)) != cudaSuccess) return -1;
+  if (v) cudaMemcpyToSymbol(g_tma_fail, &zero, sizeof(int));
+  return v;
 }
 
 extern "C" int kge_fused_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,

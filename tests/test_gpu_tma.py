@@ -80,3 +80,36 @@ def test_tma_forward_is_bit_identical(name, Nn, R, D, B, K, mode):
             got = _forward(m, s, n, w, mode)
         for a, b, what in zip(got, ref, ("coef_pos", "coef_neg", "pos_score", "neg_score", "stats")):
             assert torch.equal(a, b), (what, minb, stages, (a - b).abs().max().item())
+
+
+def _backward(m, s, n, mode, cp, cn, stats):
+    ge, gr = torch.zeros_like(m.entity_embedding.data), torch.zeros_like(m.relation_embedding.data)
+    ops.fused_backward_raw(m.spec, m.entity_embedding.data, m.relation_embedding.data, s, n, mode, cp, cn, stats, ge, gr)
+    torch.cuda.synchronize()
+    return ge, gr
+
+
+@pytest.mark.parametrize("name,Nn,R,D,B,K", SHAPES)
+@pytest.mark.parametrize("mode", ("tail-batch", "head-batch"))
+def test_tma_backward_matches_scatter_kernel(name, Nn, R, D, B, K, mode):
+    """K3-TMA (bulk loads in, cp.reduce.async.bulk adds out) against K3 (LDG + RED.128): same gradients up to
+    the order in which floating-point adds land (both are atomic scatters)."""
+    m, s, n, w = _problem(name, Nn, R, D, B, K, seed=3)
+    with _env(KGE_FWD_TMA=0):
+        cp, cn, _, _, stats = _forward(m, s, n, w, mode)
+    with _env(KGE_BWD_TMA=0):
+        ge_ref, gr_ref = _backward(m, s, n, mode, cp, cn, stats)
+    for stages in (0, 1):
+        with _env(KGE_BWD_TMA=1, KGE_TMA_STAGES=stages):
+            ge, gr = _backward(m, s, n, mode, cp, cn, stats)
+        assert ops.N.load().kge_tma_fail_flag() == 0, "a TMA wait timed out"
+        for got, ref, what in ((ge, ge_ref, "entity"), (gr, gr_ref, "relation")):
+            scale = ref.abs().max().item()
+            err = (got - ref).abs().max().item()
+            assert err <= 2e-5 * scale, (what, stages, err, scale)
+        # rows nobody touched stay exactly zero (a bulk reduction must not spill over its row)
+        touched = torch.zeros(Nn, dtype=torch.bool, device=DEV)
+        touched[n.flatten()] = True
+        touched[s[:, 0]] = True
+        touched[s[:, 2]] = True
+        assert not ge[~touched].any()
