@@ -30,6 +30,9 @@
 #ifndef KGE_FWD_U
 #define KGE_FWD_U 2  // 16-byte chunks in flight per row per lane
 #endif
+#ifndef KGE_BWD_BULK_DEFAULT
+#define KGE_BWD_BULK_DEFAULT 0  // 1: K3b (bulk-reduction row gradients) unless KGE_BWD_BULK=0
+#endif
 
 namespace kge {
 
@@ -332,16 +335,44 @@ constexpr int kTileK = 256;
 // DQONLY (pass 1 of the by-entity backward, byent.cu): the candidates' row gradients are NOT scattered —
 // pass 2 forms them entity by entity without atomics — and the head / tail gradient rows of each positive
 // are stored to per-positive buffers instead of being added into the gradient table.
-template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false>
+// BULK (K3b, the default for 16-byte-aligned unsharded launches): a candidate row's gradient is not fired as
+// 16 RED.128 per lane but written to a shared-memory staging row and added into the gradient table by ONE bulk
+// reduction (cp.reduce.async.bulk.global.shared::cta.add.f32, the TMA's reduce path).  ncu showed K3 limited by the
+// L1/TEX pipe, which serialises vector REDs at a fraction of its load rate; the staging stores are plain STS.128
+// and the reduction itself bypasses L1.  Loads stay LDG.128 (the all-TMA variant in score_tma.cuh lost to this
+// kernel: 8 KB of shared memory per row in flight caps the resident warps).  One named barrier per row and group.
+constexpr int kBulkSlots = 4;  // staging rows per thread group
+
+// Named barrier of thread group `grp` (tpg threads).  Literal barrier ids: a register id would make ptxas
+// reserve all 16 hardware barriers for the CTA.
+__device__ __forceinline__ void group_barrier(int grp, int tpg) {
+  switch (grp) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"r"(tpg) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"r"(tpg) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"r"(tpg) : "memory"); break;
+    case 3: asm volatile("bar.sync 4, %0;" ::"r"(tpg) : "memory"); break;
+    case 4: asm volatile("bar.sync 5, %0;" ::"r"(tpg) : "memory"); break;
+    case 5: asm volatile("bar.sync 6, %0;" ::"r"(tpg) : "memory"); break;
+    case 6: asm volatile("bar.sync 7, %0;" ::"r"(tpg) : "memory"); break;
+    default: asm volatile("bar.sync 8, %0;" ::"r"(tpg) : "memory"); break;
+  }
+}
+
+template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false, bool BULK = false>
 __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
   using T = Traits<M>;
-  extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC]
+  static_assert(!BULK || (VEC == 4 && !SHARD && !DQONLY), "bulk reduction: aligned, local, scattering launches only");
+  extern __shared__ __align__(16) float smem[];  // cross-group dq buffer: [G-1][NC][tpg*VEC] (+ BULK: staging rows)
   __shared__ int64_t s_idx[kTileK];
   __shared__ float s_coef[kTileK];
 
   const int tid = threadIdx.x;
   const int tpg = p.tpg, G = kThreads / tpg;
   const int grp = tid / tpg, lt = tid - grp * tpg;
+  // BULK: this group's ring of staging rows ([re | im] like a gradient row) behind the dq buffer
+  const int stage_floats = T::NC * p.D;
+  float* stage = smem + (size_t)(G - 1) * T::NC * tpg * VEC + (size_t)grp * kBulkSlots * stage_floats;
+  int slot = 0;
   int64_t i = blockIdx.x;
   size_t roff = 0;
   if (p.rec_B > 0) {
@@ -403,14 +434,14 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
         s_coef[k] = scale * gnegrow[jt + k];
       }
       __syncthreads();
-      if (active) {
+      if (active || BULK) {  // BULK: idle lanes of a group still take part in its per-row barrier
         constexpr int U = 4;
         for (int jj = grp; jj < n; jj += G * U) {
-          float e0[U][VEC], e1[U][VEC];
+          float e0[U][VEC] = {}, e1[U][VEC] = {};
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int k = jj + u * G;
-            if (k < n) {
+            if (k < n && active) {
               const float* row = ent_row<SHARD>(p, s_idx[k]) + p.col0;
               ld_global<VEC>(row + d, e0[u]);
               if constexpr (T::NC == 2) ld_global<VEC>(row + p.im_off + d, e1[u]);
@@ -422,14 +453,35 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
             if (k < n) {
               const float c = s_coef[k];
               float* grow = grad_row<SHARD>(p, s_idx[k]);
-              float g0[VEC], g1[VEC];
+              float g0[VEC] = {}, g1[VEC] = {};
+              if (active) {
 #pragma unroll
-              for (int v = 0; v < VEC; ++v)
-                cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
-                            dq0[v], dq1[v], p.phase_div);
-              if constexpr (!DQONLY) {
-                red_row<VEC, SHARD>(p, grow + d, g0);
-                if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
+                for (int v = 0; v < VEC; ++v)
+                  cand_bwd<M>(q0[v], q1[v], e0[u][v], T::NC == 2 ? e1[u][v] : 0.f, c, g0[v], g1[v],
+                              dq0[v], dq1[v], p.phase_div);
+              }
+              if constexpr (BULK) {
+                float* stg = stage + (size_t)slot * stage_floats;
+                if (active) {
+                  st_shared<VEC>(stg + d, g0);
+                  if constexpr (T::NC == 2) st_shared<VEC>(stg + p.D + d, g1);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging row -> visible to the TMA
+                // the reduction that last used the NEXT slot has finished reading it (<= kBulkSlots - 2 pending)
+                if (lt == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkSlots - 2) : "memory");
+                group_barrier(grp, tpg);
+                if (lt == 0) {
+                  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(grow),
+                               "r"((uint32_t)__cvta_generic_to_shared(stg)), "r"((uint32_t)(stage_floats * 4))
+                               : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                slot = (slot + 1 == kBulkSlots) ? 0 : slot + 1;
+              } else if constexpr (!DQONLY) {
+                if (active) {
+                  red_row<VEC, SHARD>(p, grow + d, g0);
+                  if constexpr (T::NC == 2) red_row<VEC, SHARD>(p, grow + p.g_im_off + d, g1);
+                }
               }
             }
           }
@@ -550,6 +602,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
       red_add<VEC>(gr + d, gr0);
       if constexpr (T::RC == 2) red_add<VEC>(gr + p.g_im_off + d, gr1);
     }
+  }
+  if constexpr (BULK) {  // every bulk reduction this thread issued has been performed before the CTA retires
+    if (lt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 
@@ -679,9 +734,9 @@ static void fill_fwd(FwdParams& p, const kge_tables_t* t, const kge_shards_t* sh
   p.modulus = t->modulus;
 }
 
-template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false>
+template <int M, bool HEAD, int VEC, bool SHARD = false, bool DQONLY = false, bool BULK = false>
 static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = score_bwd_kernel<M, HEAD, VEC, SHARD, DQONLY>;
+  auto kern = score_bwd_kernel<M, HEAD, VEC, SHARD, DQONLY, BULK>;
   int rc = set_smem(kern, smem);
   if (rc) return rc;
   kern<<<grid, kThreads, smem, st>>>(p);
@@ -843,6 +898,24 @@ static int run_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64
   case MM:                                                                            \
     return mode == KGE_HEAD_BATCH ? launch_bwd<MM, true, 4, true>(p, grid, smem, st)  \
                                   : launch_bwd<MM, false, 4, true>(p, grid, smem, st);
+    switch (t->model) {
+      KGE_CASE(KGE_TRANSE)
+      KGE_CASE(KGE_DISTMULT)
+      KGE_CASE(KGE_COMPLEX)
+      KGE_CASE(KGE_ROTATE)
+      KGE_CASE(KGE_PROTATE)
+    }
+#undef KGE_CASE
+    return KGE_E_MODEL;
+  }
+  // K3b: row gradients through shared-memory staging rows + one bulk reduction per row (see score_bwd_kernel)
+  const bool bulk = vec && p.K > 0 && p.D <= kThreads * 4 && env_int("KGE_BWD_BULK", KGE_BWD_BULK_DEFAULT) != 0;
+  if (bulk) {
+    const size_t smem_b = smem + (size_t)G * kBulkSlots * entity_comps(t->model) * p.D * sizeof(float);
+#define KGE_CASE(MM)                                                                                       \
+  case MM:                                                                                                 \
+    return mode == KGE_HEAD_BATCH ? launch_bwd<MM, true, 4, false, false, true>(p, grid, smem_b, st)       \
+                                  : launch_bwd<MM, false, 4, false, false, true>(p, grid, smem_b, st);
     switch (t->model) {
       KGE_CASE(KGE_TRANSE)
       KGE_CASE(KGE_DISTMULT)

@@ -97,10 +97,12 @@ def test_tma_backward_matches_scatter_kernel(name, Nn, R, D, B, K, mode):
     m, s, n, w = _problem(name, Nn, R, D, B, K, seed=3)
     with _env(KGE_FWD_TMA=0):
         cp, cn, _, _, stats = _forward(m, s, n, w, mode)
-    with _env(KGE_BWD_TMA=0):
+    with _env(KGE_BWD_TMA=0, KGE_BWD_BULK=0):
         ge_ref, gr_ref = _backward(m, s, n, mode, cp, cn, stats)
-    for stages in (0, 1):
-        with _env(KGE_BWD_TMA=1, KGE_TMA_STAGES=stages):
+    for variant in ({"KGE_BWD_TMA": 1, "KGE_TMA_STAGES": 0}, {"KGE_BWD_TMA": 1, "KGE_TMA_STAGES": 1},
+                    {"KGE_BWD_BULK": 1, "KGE_BWD_TMA": 0}):  # K3-TMA (two ring depths), K3b (LDG in, bulk reduce out)
+        stages = variant
+        with _env(**variant):
             ge, gr = _backward(m, s, n, mode, cp, cn, stats)
         assert ops.N.load().kge_tma_fail_flag() == 0, "a TMA wait timed out"
         for got, ref, what in ((ge, ge_ref, "entity"), (gr, gr_ref, "relation")):
