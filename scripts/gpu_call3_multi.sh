@@ -17,7 +17,7 @@ for cfg in cfg2 cfg4; do
 done
 # the driver's own invocation (default flags, steps 20 / warmup 5)
 timeout 300 $RUN bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_driverlike_${N}gpu.json 2> $OUT/bench_driverlike_${N}gpu.err
-if [ "$N" -ge 4 ]; then
+if [ "$N" -eq 4 ]; then
   for mode in rowshard; do
     nvidia-smi nvlink -gt d -i 0 > $OUT/nvlink_cfg4_${N}gpu_${mode}_before.txt 2>&1
     timeout 300 $RUN bench.py --gpus $N --config cfg4 --steps 100 --warmup 10 --mode $mode \
