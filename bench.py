@@ -488,17 +488,24 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm (value) ----------------
-    for i in range(warmup):
+    # W warm-up steps, the last three of them enqueued AFTER the barrier and right before t0: the host-side barrier,
+    # the status check and the event set-up leave the GPUs idle for milliseconds (clocks drop, and ranks leave the
+    # barrier up to a few ms apart), which a short timed region would otherwise absorb as "slow first steps" —
+    # seen as value > e2e per step at 4 / 8 GPUs.  The steps themselves keep the ranks in lockstep (flag handshakes).
+    late = min(3, warmup)
+    for i in range(warmup - late):
         trainer.step(dev_samples[i], dev_weights[i], modes[i])
     ns.check_status(dev)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _native.launches
+    for e in (t0, t1, *[x for row in ev for x in row]):
+        e.record()  # create the CUDA events now, not inside the timed region
     barrier()
+    for i in range(warmup - late, warmup):
+        trainer.step(dev_samples[i], dev_weights[i], modes[i])
     if dist:
-        # the host-side barrier leaves the ranks up to a few ms apart; a collective enqueued right before t0 lines
-        # the DEVICE timelines up, so the timed region holds K steps and not the slowest host's start-up skew
-        torch.distributed.all_reduce(torch.zeros(1, device=dev))
+        torch.distributed.all_reduce(torch.zeros(1, device=dev))  # lines the DEVICE timelines up right before t0
+    launches0 = _native.launches
     with ClockSampler(local) as clocks:
         t0.record()
         for i in range(steps):
@@ -511,10 +518,9 @@ def run_ours(args):
     ms_total = t0.elapsed_time(t1)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
-    try:  # the single-GPU flow also brackets the two Adam launches
-        adam_ms = float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
-    except Exception:
-        adam_ms = None
+    # the single-GPU / all-reduce / column-parallel flows also bracket the Adam launches
+    adam_ms = (float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
+               if trainer.mode in ("single", "allreduce", "colpar") and not trainer.pooled_gemm else 0.0)
     final_loss = trainer.loss()
     ns.check_status(dev)
 
@@ -569,10 +575,10 @@ def run_ours(args):
     if dist:
         torch.distributed.all_reduce(e2e_passes_t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(e2e_passes_t.median().item()) * steps  # median over passes of the max over ranks
-    t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, fwd_ms, bwd_ms, adam_ms], dtype=torch.float64, device=dev)
     if dist:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_total, e2e_ms, fwd_ms, bwd_ms = t.tolist()
+    ms_total, e2e_ms, fwd_ms, bwd_ms, adam_ms = t.tolist()
     triples_per_step = B * (1 + K) * world
     value = triples_per_step * steps / (ms_total * 1e-3)
     e2e_value = triples_per_step * steps / (e2e_ms * 1e-3)
@@ -585,10 +591,15 @@ def run_ours(args):
                                bwd_b, bwd_ms, hbm, peak_src)
         roof["share_of_step"] = bwd_ms / (ms_total / steps)
         roof["also"] = kernel_roofline(cfg, "fwd", "score_neg_kernel<FUSED> (fused forward, K2)", fwd_b, fwd_ms, hbm, peak_src)
-        if adam_ms:
+        if adam_ms and not dist:
             roof["adam"] = kernel_roofline(cfg, "adam", "adam_kernel x2 (dense Adam + gradient zeroing, both tables)",
                                            7 * (N * row_bytes(mname, D)[0] + R * row_bytes(mname, D)[1]),
                                            adam_ms, hbm, peak_src)
+        # where the step goes (CUDA events, max over ranks): what is neither forward, backward nor optimizer is the
+        # sampler plus, on several GPUs, the record push and the flag handshakes
+        roof["step_breakdown_ms"] = {"forward": fwd_ms, "backward": bwd_ms,
+                                     "optimizer" + ("+table all-gather over NVLink" if dist else ""): adam_ms or None,
+                                     "sampler, handshakes, launch gaps": ms_total / steps - fwd_ms - bwd_ms - (adam_ms or 0.0)}
         row_e, row_r = row_bytes(mname, D)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,

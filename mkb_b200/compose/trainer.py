@@ -528,11 +528,15 @@ class DeviceTrainer:
         if h:
             h[3].record()
         b1, b2 = self.betas
+        if h and len(h) > 5:
+            h[4].record()
         if self.ncols > 0:
             for reps, g, m, v, comps, tbl in ((self._replicas[0], self.g_ent, self.m_ent, self.v_ent, self.nc, self.ent),
                                               (self._replicas[1], self.g_rel, self.m_rel, self.v_rel, self.rc, self.rel)):
                 ops.adam_slice_bcast(reps, self.rank, g, m, v, tbl.shape[0], comps, self.ncols, self.col0,
                                      tbl.shape[1], self.D, self.t, self.lr, b1, b2, self.eps, device=self.dev)
+        if h and len(h) > 5:
+            h[5].record()
         # every replica must hold every slice before anyone's next forward reads the tables
         if peer:
             ops.peer_signal(self._flag_ptrs[1], self.rank, self.t, self.dev)  # waited for at the next step's start

@@ -609,7 +609,9 @@ __global__ void __launch_bounds__(kThreads, 3) score_bwd_kernel(BwdParams p) {
 }
 
 }  // namespace kge
+#ifndef KGE_NO_TMA  // (the host-side emulation of the kernels in tests/emu builds without the TMA variants)
 #include "score_tma.cuh"  // K2-TMA / K3-TMA: the fused forward and backward with rows staged through the TMA
+#endif
 namespace kge {
 
 // ------------------------------------------------------------------------------------------------
@@ -744,6 +746,7 @@ static int launch_bwd(const BwdParams& p, dim3 grid, size_t smem, cudaStream_t s
   return KGE_OK;
 }
 
+#ifndef KGE_NO_TMA
 // K3-TMA launcher (score_tma.cuh): KGE_E_UNSUPPORTED when the shape does not fit (caller uses the scatter kernel).
 template <int M, bool HEAD, int UMAX>
 static int launch_bwd_tma(const BwdParams& p, int stages, int n_slices, size_t smem, int grid, cudaStream_t st) {
@@ -789,6 +792,10 @@ static int run_bwd_tma(const kge_tables_t* t, int mode, const BwdParams& p, int 
 #undef KGE_TMA_CASE2
   return KGE_E_MODEL;
 }
+
+#else
+static int run_bwd_tma(const kge_tables_t*, int, const BwdParams&, int, cudaStream_t) { return KGE_E_UNSUPPORTED; }
+#endif
 
 // col0 / ncols select a column chunk of the hidden dim; ncols <= 0 means the whole row, in which case
 // the gradient buffers have the tables' own layout.  With a chunk, grad_ent / grad_rel are dense
@@ -1040,6 +1047,7 @@ extern "C" size_t kge_loss_workspace_bytes(int64_t B) {
   return (size_t)(3 * (B > 0 ? B : 0)) * sizeof(float) + 16;
 }
 
+#ifndef KGE_NO_TMA
 // K2-TMA launcher (score_tma.cuh).  Returns KGE_E_UNSUPPORTED when the shape does not fit the variant
 // (the caller then uses the LDG kernel).
 template <int M, bool HEAD, int UMAX, int MINB>
@@ -1090,6 +1098,10 @@ static int run_fwd_tma(const kge_tables_t* t, int mode, const FwdParams& p, int*
   return KGE_E_MODEL;
 }
 
+#else
+static int run_fwd_tma(const kge_tables_t*, int, const FwdParams&, int*, cudaStream_t) { return KGE_E_UNSUPPORTED; }
+#endif
+
 extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,
                              const int64_t* neg, int64_t K, const float* weight, float alpha,
                              float* pos_score, float* neg_score, float* coef_pos, float* coef_neg,
@@ -1126,10 +1138,14 @@ extern "C" int kge_fused_fwd(const kge_tables_t* t, int mode, const int64_t* sam
 }
 
 extern "C" int kge_tma_fail_flag(void) {
+#ifndef KGE_NO_TMA
   int v = 0, zero = 0;
   if (cudaMemcpyFromSymbol(&v, g_tma_fail, sizeof(int)) != cudaSuccess) return -1;
   if (v) cudaMemcpyToSymbol(g_tma_fail, &zero, sizeof(int));
   return v;
+#else
+  return 0;
+#endif
 }
 
 extern "C" int kge_fused_bwd(const kge_tables_t* t, int mode, const int64_t* sample, int64_t B,

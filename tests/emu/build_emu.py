@@ -163,6 +163,9 @@ def rewrite_asm(text):
             code = f"{outs[0]} = sqrtf({ins[0]});"
         elif ptx.startswith("rsqrt.approx"):
             code = f"{outs[0]} = 1.0f / sqrtf({ins[0]});"
+        elif re.match(r"(bar\.sync \d|fence\.proxy\.async|cp\.async\.bulk|cp\.reduce\.async\.bulk)", ptx):
+            # K3b's staged bulk reductions (score.cu, opt-in with KGE_BWD_BULK=1) have no host model
+            code = '{ fprintf(stderr, "cuda_emu: TMA bulk / named-barrier PTX is not emulated (KGE_BWD_BULK)\\n"); abort(); }'
         elif "globaltimer" in ptx:  # nanosecond wall clock
             code = (f"{{ struct timespec _ts; clock_gettime(CLOCK_MONOTONIC, &_ts); "
                     f"{outs[0]} = (long long)_ts.tv_sec * 1000000000LL + _ts.tv_nsec; }}")
@@ -179,6 +182,8 @@ def preprocess(name):
     text = open(os.path.join(CSRC, name)).read()
     text = text.replace('#include "../../include/kge_b200.h"', f'#include "{os.path.join(ROOT, "include", "kge_b200.h")}"')
     text = rewrite_asm(rewrite_static_shared(rewrite_extern_shared(rewrite_launches(text))))
+    if name == "score.cu":
+        text = "#define KGE_NO_TMA 1  // score_tma.cuh (cp.async.bulk / mbarrier) is not emulated\n" + text
     return f"// GENERATED by tests/emu/build_emu.py from mkb_b200/csrc/{name} — do not edit\n" + text
 
 
