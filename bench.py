@@ -520,7 +520,7 @@ def run_ours(args):
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     # the single-GPU / all-reduce / column-parallel flows also bracket the Adam launches
     adam_ms = (float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
-               if trainer.mode in ("single", "allreduce", "colpar") and not trainer.pooled_gemm else 0.0)
+               if trainer.mode in ("single", "allreduce", "colpar", "colshard") and not trainer.pooled_gemm else 0.0)
     final_loss = trainer.loss()
     ns.check_status(dev)
 
@@ -622,6 +622,10 @@ def run_ours(args):
                     f"and Adam state each); remote rows gathered by P2P loads, row gradients added into the owner's "
                     f"shard by system-scope vector REDs over NVLink; relation gradient all-reduced"
                     if trainer.mode == "rowshard" else
+                    f"tp{world} over the hidden dim: each GPU holds 1/{world} of the COLUMNS of both tables (and of gradient "
+                    f"and Adam state), scores the global batch over its columns, one all-reduce of the partial scores; "
+                    f"no table or gradient row crosses NVLink"
+                    if trainer.mode == "colshard" else
                     f"dp{world}, replicated tables; all-reduce of 3 loss sums + dense gradients" + (
                         f" [{trainer.mode_note}]" if trainer.mode_note else "")),
                 "l2": "working set per step (tables+grads+Adam moments = "
@@ -635,6 +639,9 @@ def run_ours(args):
                         if trainer.mode in ("single", "allreduce") else
                         "sample_negatives + fused_fwd_sharded + fused_bwd_sharded + adam(own shard(s)) + adam(relation)"
                         if trainer.mode == "rowshard" else
+                        "sample_negatives + push batch blocks + 2 x score_fwd(sub-table, global batch) + all-reduce(partial "
+                        "scores) + adv_loss fwd/bwd + fused_bwd(sub-table) + 2 x adam(own columns)"
+                        if trainer.mode == "colshard" else
                         (f"wait(slices) + sample_negatives + fused_fwd + peer_copy(record) + signal + wait(records) + "
                          f"1 multi-record fused_bwd_chunk + 2 x adam_slice_bcast + signal" if trainer.handshake == "peer" else
                          f"sample_negatives + fused_fwd + all-gather(step records) + {world} x fused_bwd_chunk + "
@@ -701,10 +708,11 @@ def main():
                     help="skip the short config-4 run that adds roofline_hbm_config to the line")
     ap.add_argument("--cpu-budget", type=float, default=150.0,
                     help="--impl reference: seconds of CPU work the bounded sample is sized for (all steps together)")
-    ap.add_argument("--mode", default=None, choices=["colpar", "allreduce", "rowshard"],
+    ap.add_argument("--mode", default=None, choices=["colpar", "allreduce", "rowshard", "colshard"],
                     help="multi-GPU scheme of DeviceTrainer (default colpar: column-parallel backward + fused "
                          "Adam/all-gather over NVLink peer memory; allreduce: dense gradient all-reduce; rowshard: "
-                         "entity table row-sharded over the GPUs, P2P row gathers + remote gradient REDs)")
+                         "entity table row-sharded over the GPUs, P2P row gathers + remote gradient REDs; colshard: tables "
+                         "sharded by hidden-dim columns, partial scores all-reduced, nothing else moves)")
     ap.add_argument("--backward", default="scatter", choices=["scatter", "by_entity"],
                     help="single-GPU backward: scatter = K3 vector REDs + dense Adam (default, the measured path); "
                          "by_entity = atomics-free per-entity backward with Adam fused in (csrc/byent.cu)")

@@ -34,6 +34,17 @@ positives).  Two schemes:
     tables fit one GPU many times over and (G-1)/G of all gathers would cross NVLink (~8x slower than
     HBM), so this is not the default; see DESIGN.md §6.
 
+``colshard`` (opt-in; the scheme for tables that do not fit one GPU — or whose per-step all-gather would dominate)
+    — the tables are sharded by COLUMNS of the hidden dim (tensor parallel): rank r holds columns slice r of EVERY
+    row (1/G of table, gradient and Adam state) and never sees the rest.  Every score of the five models is a sum
+    over the hidden dim (L1 / complex-modulus distances, dot products), so each rank computes the PARTIAL scores of
+    the global batch over its columns (K1 on its sub-table, full-speed local HBM reads), one all-reduce sums the
+    [G*B, 1+K] partial scores (4-8 MB: the only bytes that cross NVLink besides the ~2 MB batch records), every rank
+    forms loss and per-score gradients of the global batch redundantly, runs the fused backward on its sub-table and
+    Adam on its slice.  No table row, gradient row or updated column ever moves: where ``colpar`` ships the whole
+    updated table over NVLink every step (493 MB at config 4: 0.5 ms) and ``rowshard`` pulls every remote row,
+    this scheme moves a few MB.  See DESIGN.md §6 for the measurements and which scheme suits which table size.
+
 In all of them, every rank normalises by the GLOBAL sum of weights (losses/adversarial.py:28-30 over the
 global batch): the three loss sums are all-reduced between forward and backward.
 
@@ -78,7 +89,7 @@ class DeviceTrainer:
         # a stock torch.optim.Adam (the optimizer of the reference's quick-start, README.md:123-126) keeps its
         # step count as a float32 CPU tensor; optim.DenseAdam as an int
         t._step_as_tensor = type(optimizer) is torch.optim.Adam
-        if t.mode not in ("colpar", "rowshard"):
+        if t.mode not in ("colpar", "rowshard", "colshard"):
             for p, m, v in ((model.entity_embedding, t.m_ent, t.v_ent), (model.relation_embedding, t.m_rel, t.v_rel)):
                 st = optimizer.state[p]
                 if st:
@@ -129,6 +140,8 @@ class DeviceTrainer:
             raise ValueError("virtual_shards is a single-process mode")
         if mode is None:
             mode = "rowshard" if self.virtual_shards else ("colpar" if self.distributed else "single")
+        if mode == "colshard" and (not self.distributed or D % 4 != 0 or D < 32 * self.world):
+            raise ValueError("colshard needs torch.distributed, hidden_dim % 4 == 0 and >= 32 columns per rank")
         if not self.distributed and mode != "rowshard":
             mode = "single"
         if mode == "colpar" and (D % 4 != 0 or D < 32 * self.world or self.world > 16):
@@ -181,7 +194,11 @@ class DeviceTrainer:
         self.backward = backward if mode == "single" else "scatter"
         if self.backward == "by_entity" and D % 4 != 0:
             raise ValueError("backward='by_entity' needs hidden_dim % 4 == 0")
-        if mode == "rowshard":
+        if mode == "colshard":
+            if self.modulus is not None:
+                raise NotImplementedError("pRotatE runs on the single-GPU DeviceTrainer flow only")
+            self._setup_colshard(model, f32)
+        elif mode == "rowshard":
             self._setup_rowshard(model, f32, scalar_red)
         elif mode == "colpar":
             self._setup_colpar(f32)
@@ -287,6 +304,119 @@ class DeviceTrainer:
         self._tiny = torch.zeros(1, **f32)
 
     # ------------------------------------------------------------------------------------------
+    # colshard: tables sharded by columns of the hidden dim
+    # ------------------------------------------------------------------------------------------
+    def _setup_colshard(self, model, f32):
+        import torch.distributed._symmetric_memory as symm
+
+        G, r, B, K = self.world, self.rank, self.max_batch, self.K
+        self.col0, self.ncols = _column_slices(self.D, G)[r]
+        w = self.ncols
+        if w <= 0 or w % 4:
+            raise ValueError(f"colshard: rank {r} would own {w} columns of {self.D}")
+        full_e, full_r = model.entity_embedding.data, model.relation_embedding.data
+        N_, R_ = full_e.shape[0], full_r.shape[0]
+        cut = lambda t, comps: t.view(t.shape[0], comps, self.D)[:, :, self.col0:self.col0 + w].reshape(t.shape[0], comps * w).contiguous()
+        self.ent_loc, self.rel_loc = cut(full_e, self.nc), cut(full_r, self.rc)
+        # a model of hidden_dim = w over this rank's columns; embedding_range (RotatE's phase divisor) stays global
+        self.spec_loc = ops.TableSpec(self.spec.model_name, w, self.spec.gamma, self.spec.embedding_range)
+        self.g_ent, self.g_rel = torch.zeros_like(self.ent_loc), torch.zeros_like(self.rel_loc)
+        self.m_ent, self.v_ent = torch.zeros_like(self.ent_loc), torch.zeros_like(self.ent_loc)
+        self.m_rel, self.v_rel = torch.zeros_like(self.rel_loc), torch.zeros_like(self.rel_loc)
+        # the global batch (G blocks of B positives: triples, negatives, weights) + two flag arrays, symmetric
+        al = lambda x: (x + 15) // 16 * 16
+        o_neg = al(G * B * 24)
+        o_w = o_neg + al(G * B * K * 8)
+        o_flags = o_w + al(G * B * 4)
+        buf = symm.empty(o_flags + 128, dtype=torch.uint8, device=self.dev)
+        buf.zero_()
+        torch.cuda.synchronize(self.dev)
+        group = self.group if self.group is not None else torch.distributed.group.WORLD
+        hdl = symm.rendezvous(buf, group)
+        self._symm = [hdl]
+        ptrs = [int(x) for x in hdl.buffer_ptrs]
+        if len(ptrs) != G or ptrs[r] != buf.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory pointer table")
+        self._gb_ptrs = ptrs
+        self._gb_off = (0, o_neg, o_w)
+        self.sample_all = buf[: G * B * 24].view(torch.int64).view(G * B, 3)
+        self.neg_all = buf[o_neg: o_neg + G * B * K * 8].view(torch.int64).view(G * B, K)
+        self.weight_all = buf[o_w: o_w + G * B * 4].view(torch.float32)
+        self._flag_ptrs = [[p + o_flags + 64 * ph for p in ptrs] for ph in (0, 1)]
+        self._flags = [buf[o_flags + 64 * ph: o_flags + 64 * ph + 64].view(torch.int32) for ph in (0, 1)]
+        self._peer_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.neg = self.neg_all[r * B:(r + 1) * B]  # the sampler writes this rank's block in place
+        # partial scores of the global batch, negatives first then positives: ONE all-reduce
+        self._sc = torch.zeros(G * B * (K + 1), **f32)
+        self._sc_neg, self._sc_pos = self._sc[: G * B * K].view(G * B, K), self._sc[G * B * K:]
+        self._g_neg, self._g_pos = torch.zeros(G * B, K, **f32), torch.zeros(G * B, **f32)
+        self._loss_ws = torch.zeros(max(ops.N.load().kge_loss_workspace_bytes(G * B), 64), dtype=torch.uint8,
+                                    device=self.dev)
+        self._unit_stats = torch.tensor([0.0, 0.0, 0.5, 0.0], **f32)  # scale 1 / (2 * 0.5): gradients arrive final
+        self.coef_pos = self.coef_neg = None
+        torch.cuda.synchronize(self.dev)
+        torch.distributed.barrier(group=self.group)
+
+    def _step_colshard(self, sample, weight, mode, h):
+        G, r, B, K = self.world, self.rank, self.max_batch, self.K
+        b = sample.shape[0]
+        if b < B:  # short last batch: weight-0 copies of row 0 add nothing to the loss sums or to any gradient
+            sample = torch.cat([sample, sample[:1].expand(B - b, -1)])
+            weight = torch.cat([weight, torch.zeros(B - b, dtype=weight.dtype, device=weight.device)])
+        self.sample_all[r * B:(r + 1) * B].copy_(sample)
+        self.weight_all[r * B:(r + 1) * B].copy_(weight)
+        self._sample(self.sample_all[r * B:(r + 1) * B], mode, self.neg)
+        # peers are done reading the previous global batch before anybody overwrites its blocks
+        ops.peer_wait(self._flags[1], G, self.t, self._peer_status)
+        for off, blk in zip(self._gb_off, (self.sample_all, self.neg_all, self.weight_all)):
+            mine = blk[r * B:(r + 1) * B]
+            nbytes = mine.numel() * mine.element_size()
+            ops.peer_copy(mine, self._gb_ptrs, r, off + r * nbytes, nbytes)
+        self.t += 1
+        ops.peer_signal(self._flag_ptrs[0], r, self.t, self.dev)
+        ops.peer_wait(self._flags[0], G, self.t, self._peer_status)
+        if h:
+            h[0].record()
+        # partial scores of the GLOBAL batch over this rank's columns (K1 on the sub-table)
+        ops.score_forward_raw(self.spec_loc, self.ent_loc, self.rel_loc, self.sample_all, None, mode, self._sc_pos)
+        ops.score_forward_raw(self.spec_loc, self.ent_loc, self.rel_loc, self.sample_all, self.neg_all, mode, self._sc_neg)
+        if h:
+            h[1].record()
+        torch.distributed.all_reduce(self._sc, group=self.group)  # the path's one real exchange: sum over column slices
+        if self.spec.model_name in ("TransE", "RotatE", "pRotatE"):
+            self._sc.sub_((G - 1) * self.spec.gamma)  # every partial carried its own "gamma -"
+        ops.adversarial_loss_raw(self._sc_pos, self._sc_neg, self.weight_all, self.alpha, self.stats, self._loss_ws,
+                                 self._g_pos, self._g_neg)
+        if h:
+            h[2].record()
+        ops.fused_backward_raw(self.spec_loc, self.ent_loc, self.rel_loc, self.sample_all, self.neg_all, mode,
+                               self._g_pos, self._g_neg, self._unit_stats, self.g_ent, self.g_rel)
+        if h:
+            h[3].record()
+        ops.peer_signal(self._flag_ptrs[1], r, self.t, self.dev)  # "I am done with this global batch"
+        b1, b2 = self.betas
+        if h and len(h) > 5:
+            h[4].record()
+        ops.adam_step(self.ent_loc, self.g_ent, self.m_ent, self.v_ent, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        ops.adam_step(self.rel_loc, self.g_rel, self.m_rel, self.v_rel, self.t, self.lr, b1, b2, self.eps, zero_grad=True)
+        if h and len(h) > 5:
+            h[5].record()
+        return self.stats
+
+    def _gather_columns(self, local, comps, out):
+        """All-gather the ranks' column slices of a table into the full [rows, comps * D] layout."""
+        G = self.world
+        widths = [w for _, w in _column_slices(self.D, G)]
+        wmax = max(widths)
+        pad = torch.zeros(local.shape[0], comps, wmax, dtype=local.dtype, device=self.dev)
+        pad[:, :, : self.ncols] = local.view(local.shape[0], comps, self.ncols)
+        parts = torch.empty((G,) + tuple(pad.shape), dtype=local.dtype, device=self.dev)
+        torch.distributed.all_gather_into_tensor(parts, pad, group=self.group)
+        full = out.view(out.shape[0], comps, self.D)
+        for rr, (c0, w) in enumerate(_column_slices(self.D, G)):
+            full[:, :, c0:c0 + w] = parts[rr][:, :, :w]
+
+    # ------------------------------------------------------------------------------------------
     # rowshard set-up
     # ------------------------------------------------------------------------------------------
     def _setup_rowshard(self, model, f32, scalar_red):
@@ -341,6 +471,10 @@ class DeviceTrainer:
         """Write the trained shards back into ``model.entity_embedding`` (all-gather in the distributed
         case) so evaluation / save / the user's own code see the current table."""
         self.flush()
+        if self.mode == "colshard":
+            self._gather_columns(self.ent_loc, self.nc, self.model.entity_embedding.data)
+            self._gather_columns(self.rel_loc, self.rc, self.model.relation_embedding.data)
+            return
         if self.mode != "rowshard":
             return
         full = self.model.entity_embedding.data
@@ -423,6 +557,8 @@ class DeviceTrainer:
         B = sample.shape[0]
         if B > self.max_batch:
             raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        if self.mode == "colshard":
+            return self._step_colshard(sample, weight, mode, self.hooks)
         neg = self.neg[:B]
         coef_pos, coef_neg = self.coef_pos[:B], self.coef_neg[:B]
         self._sample(sample, mode, neg)
@@ -550,7 +686,7 @@ class DeviceTrainer:
         """colpar/peer: hold the stream until every peer's slice of the LAST step is in this replica (the next
         step would do it; callers that read the tables — evaluation, save — need it now), then check that no
         handshake timed out (synchronises)."""
-        if self.handshake == "peer":
+        if self.handshake == "peer" or self.mode == "colshard":
             ops.peer_wait(self._flags[1], self.world, self.t, self._peer_status)
             bad = int(self._peer_status.item())
             if bad:

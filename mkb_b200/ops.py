@@ -445,6 +445,28 @@ def adam_slice_bcast(replica_ptrs, self_index, grad_slice, m_slice, v_slice, row
     N.count_launch()
 
 
+def score_forward_raw(spec, ent, rel, sample, neg, mode, out):
+    """K1 into a caller-owned buffer: out[B] = model(sample) when ``neg`` is None, else out[B,K]."""
+    lib = N.load()
+    tb = spec.struct(ent, rel)
+    N.check(lib.kge_score_fwd(C.byref(tb), _mode_id(mode), N.ptr(sample), sample.shape[0], N.ptr(neg),
+                              0 if neg is None else neg.shape[1], N.ptr(out), N.stream_ptr(ent.device)), "kge_score_fwd")
+    N.count_launch()
+
+
+def adversarial_loss_raw(pos, neg, weight, alpha, stats, ws, grad_pos, grad_neg):
+    """Stand-alone self-adversarial loss, forward + backward, into caller-owned buffers: stats[4] = (S_p, S_n, W,
+    loss), grad_pos[B] / grad_neg[B,K] = dL/dscore (already carrying 1/(2W))."""
+    lib = N.load()
+    B, K = neg.shape
+    st = N.stream_ptr(neg.device)
+    N.check(lib.kge_adv_loss_fwd(N.ptr(pos), N.ptr(neg), N.ptr(weight), B, K, alpha, N.ptr(stats), N.ptr(ws), st),
+            "kge_adv_loss_fwd")
+    N.check(lib.kge_adv_loss_bwd(N.ptr(pos), N.ptr(neg), N.ptr(weight), B, K, alpha, N.ptr(stats), None,
+                                 N.ptr(grad_pos), N.ptr(grad_neg), st), "kge_adv_loss_bwd")
+    N.count_launch(2)
+
+
 def peer_copy(src, dst_ptrs, self_index, dst_offset_bytes, nbytes=None):
     """``src`` (contiguous device tensor) -> every peer's buffer at ``dst_offset_bytes`` (NVLink stores)."""
     lib = N.load()

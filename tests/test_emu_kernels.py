@@ -14,6 +14,7 @@ import pytest
 
 from conftest import MODELS, MODES, score_tol
 from emu import harness as H
+from mkb_b200 import _native as N
 from oracle import kge_oracle as ko
 
 
@@ -764,3 +765,60 @@ def test_peer_handshake_primitives():
     assert status[0] == 1 << 1
     assert l.kge_peer_copy(H.P(src), arr, G, 1, 8, rec, None) == -5
     assert l.kge_peer_wait(None, G, 1, 1, H.P(status), None) == -1
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("mode", MODES)
+def test_column_sharded_step_equals_the_full_step(model, mode):
+    """The arithmetic of DeviceTrainer(mode="colshard") with the collectives replaced by a Python sum: G sub-tables of
+    hidden-dim columns, K1 partial scores summed (minus (G-1)*gamma for the distance models), the stand-alone loss
+    for the per-score gradients, the fused backward per sub-table with unit statistics — against kge_fused_fwd /
+    kge_fused_bwd on the full tables."""
+    l = H.lib()
+    rng = np.random.RandomState(11)
+    Nn, R, D, B, K, gamma, G = 40, 4, 48, 7, 9, 9.0, 3
+    ent, rel = ko.init_tables(model, Nn, R, D, gamma, seed=2)
+    ent, rel = (ent * 3).astype(np.float32), (rel * 3).astype(np.float32)
+    nc, rc = H.NC[model], H.RC[model]
+    sample = np.stack([rng.randint(Nn, size=B), rng.randint(R, size=B), rng.randint(Nn, size=B)], 1).astype(np.int64)
+    neg = np.sort(rng.randint(Nn, size=(B, K)), axis=1).astype(np.int64)
+    w = rng.uniform(0.1, 0.5, B).astype(np.float32)
+    full = H.fused_fwd(model, ent, rel, gamma, sample, neg, w, mode)
+    ge_ref, gr_ref = H.fused_bwd(model, ent, rel, gamma, sample, neg, mode, full)
+
+    emb_range = float(np.float32((np.float32(gamma) + np.float32(2)) / np.float32(D)))  # the GLOBAL range
+    slices = [(0, 16), (16, 16), (32, 16)]
+    subs = []
+    pos, ngs = np.zeros((B, 1), np.float32), np.zeros((B, K), np.float32)
+    for c0, wd in slices:
+        cut = lambda t, comps: np.ascontiguousarray(t.reshape(t.shape[0], comps, D)[:, :, c0:c0 + wd].reshape(t.shape[0], comps * wd))
+        e_loc, r_loc = cut(ent, nc), cut(rel, rc)
+        tb = N.KgeTables(H.P(e_loc), H.P(r_loc), Nn, R, wd, N.MODEL_IDS[model], float(gamma), emb_range, None)
+        p_loc, n_loc = np.zeros((B, 1), np.float32), np.zeros((B, K), np.float32)
+        H.ok(l.kge_score_fwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, None, 0, H.P(p_loc), None))
+        H.ok(l.kge_score_fwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(n_loc), None))
+        pos += p_loc
+        ngs += n_loc
+        subs.append((tb, e_loc, r_loc))
+    if model in ("TransE", "RotatE"):
+        pos -= (G - 1) * gamma
+        ngs -= (G - 1) * gamma
+    np.testing.assert_allclose(pos, full["pos"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(ngs, full["neg"], rtol=2e-5, atol=2e-5)
+    stats = np.zeros(4, np.float32)
+    ws = np.zeros(l.kge_loss_workspace_bytes(B) + 64, np.uint8)
+    gp, gn = np.zeros(B, np.float32), np.zeros((B, K), np.float32)
+    posv = np.ascontiguousarray(pos.reshape(-1))
+    H.ok(l.kge_adv_loss_fwd(H.P(posv), H.P(ngs), H.P(w), B, K, 0.5, H.P(stats), H.P(ws), None))
+    H.ok(l.kge_adv_loss_bwd(H.P(posv), H.P(ngs), H.P(w), B, K, 0.5, H.P(stats), None, H.P(gp), H.P(gn), None))
+    np.testing.assert_allclose(stats[3], full["stats"][3], rtol=1e-5)
+    unit = np.array([0, 0, 0.5, 0], np.float32)
+    ge, gr = np.zeros_like(ent), np.zeros_like(rel)
+    for (c0, wd), (tb, e_loc, r_loc) in zip(slices, subs):
+        ge_l, gr_l = np.zeros_like(e_loc), np.zeros_like(r_loc)
+        H.ok(l.kge_fused_bwd(C.byref(tb), H.mode_id(mode), H.P(sample), B, H.P(neg), K, H.P(gp), H.P(gn), H.P(unit), None,
+                             H.P(ge_l), H.P(gr_l), None))
+        ge.reshape(Nn, nc, D)[:, :, c0:c0 + wd] = ge_l.reshape(Nn, nc, wd)
+        gr.reshape(R, rc, D)[:, :, c0:c0 + wd] = gr_l.reshape(R, rc, wd)
+    np.testing.assert_allclose(ge, ge_ref, rtol=2e-4, atol=2e-6 * np.abs(ge_ref).max())
+    np.testing.assert_allclose(gr, gr_ref, rtol=2e-4, atol=2e-6 * np.abs(gr_ref).max())

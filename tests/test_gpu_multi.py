@@ -114,6 +114,7 @@ def _worker_trainer(rank, world, port, out, mode, packed=False, handshake=None):
         opt.step()
         opt.zero_grad()
         errs.append(abs(loss.item() - tr.loss()))
+    tr.sync_model()  # colshard: gather the column slices back into the model's tables
     torch.cuda.synchronize()
     e = (m.entity_embedding - ref.entity_embedding).abs().max().item()
     r = (m.relation_embedding - ref.relation_embedding).abs().max().item()
@@ -130,7 +131,8 @@ def _worker_trainer(rank, world, port, out, mode, packed=False, handshake=None):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("mode,packed,handshake", (("colpar", False, "peer"), ("colpar", False, "nccl"),
-                                                   ("colpar", True, "nccl"), ("allreduce", False, None)))
+                                                   ("colpar", True, "nccl"), ("allreduce", False, None),
+                                                   ("colshard", False, None)))
 def test_two_gpu_trainer_matches_single_gpu(mode, packed, handshake):
     import torch.multiprocessing as mp
 
