@@ -101,6 +101,11 @@ class ClockSampler:
                 idx = int(vis.split(",")[device_index]) if vis else device_index
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # the first NVML queries of a process take milliseconds and serialise with kernel launches in the
+            # driver: pay for them here, not inside the timed region (seen as a one-off stall of the first timed
+            # steps when 4-8 ranks started polling at t0)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         except Exception as e:  # pragma: no cover
             self.nv, self.err = None, repr(e)
 
@@ -115,7 +120,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.01)
 
     def __enter__(self):
         if self.nv:
@@ -411,6 +416,8 @@ def hbm_config_run(dev, hbm, peak_src, cfg="cfg4", steps=40, warmup=5):
     torch.cuda.synchronize()
     trainer.hooks = None
     ms = t0.elapsed_time(t1) / steps
+    # per-step durations (forward-start to forward-start) as this rank saw them: a transient shows up here
+    per_step = [ev[i][0].elapsed_time(ev[i + 1][0]) for i in range(min(steps, 41) - 1)]
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     adam_ms = float(np.mean([e[4].elapsed_time(e[5]) for e in ev]))
@@ -493,6 +500,7 @@ def run_ours(args):
     # barrier up to a few ms apart), which a short timed region would otherwise absorb as "slow first steps" —
     # seen as value > e2e per step at 4 / 8 GPUs.  The steps themselves keep the ranks in lockstep (flag handshakes).
     late = min(3, warmup)
+    clock_sampler = ClockSampler(local)  # NVML handle + first queries now, polling thread only inside the region
     for i in range(warmup - late):
         trainer.step(dev_samples[i], dev_weights[i], modes[i])
     ns.check_status(dev)
@@ -506,7 +514,7 @@ def run_ours(args):
     if dist:
         torch.distributed.all_reduce(torch.zeros(1, device=dev))  # lines the DEVICE timelines up right before t0
     launches0 = _native.launches
-    with ClockSampler(local) as clocks:
+    with clock_sampler as clocks:
         t0.record()
         for i in range(steps):
             trainer.hooks = ev[i]
@@ -516,6 +524,8 @@ def run_ours(args):
     trainer.hooks = None
     launches = _native.launches - launches0
     ms_total = t0.elapsed_time(t1)
+    # per-step durations (forward-start to forward-start) as this rank saw them: a transient shows up here
+    per_step = [ev[i][0].elapsed_time(ev[i + 1][0]) for i in range(min(steps, 41) - 1)]
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
     # the single-GPU / all-reduce / column-parallel flows also bracket the Adam launches
@@ -597,6 +607,7 @@ def run_ours(args):
                                            adam_ms, hbm, peak_src)
         # where the step goes (CUDA events, max over ranks): what is neither forward, backward nor optimizer is the
         # sampler plus, on several GPUs, the record push and the flag handshakes
+        roof["per_step_ms_first_40"] = [round(x, 3) for x in per_step]
         roof["step_breakdown_ms"] = {"forward": fwd_ms, "backward": bwd_ms,
                                      "optimizer" + ("+table all-gather over NVLink" if dist else ""): adam_ms or None,
                                      "sampler, handshakes, launch gaps": ms_total / steps - fwd_ms - bwd_ms - (adam_ms or 0.0)}

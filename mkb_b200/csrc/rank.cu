@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
   const int q_base = blockIdx.x * kTQ;
-  const int64_t e_base = (int64_t)blockIdx.y * kTE;
+  // entity tiles are folded over gridDim.y x gridDim.z (grid.y alone caps at 65 535 tiles = 4.19 M entities)
+  const int64_t e_base = ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * kTE;
+  if (e_base >= p.N) return;  // the whole CTA: the folded grid may overshoot
 
   float acc[4][4];
 #pragma unroll
@@ -230,6 +232,13 @@ extern "C" size_t kge_rank_workspace_bytes(const kge_tables_t* t, int64_t Q) {
   return (size_t)Q * (row * sizeof(float) + sizeof(float) + 2 * sizeof(int64_t)) + 64;
 }
 
+// (query tiles, entity tiles) -> grid: entity tiles beyond grid.y's 65 535 spill into grid.z
+static dim3 fold_tiles(int64_t q_tiles, int64_t e_tiles) {
+  const int64_t ymax = 32768;
+  const int64_t y = e_tiles < ymax ? (e_tiles > 0 ? e_tiles : 1) : ymax;
+  return dim3((unsigned)q_tiles, (unsigned)y, (unsigned)((e_tiles + y - 1) / y > 0 ? (e_tiles + y - 1) / y : 1));
+}
+
 static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_index, int mode, const int64_t* queries,
                     int64_t Q, const kge_filter_csr_t* filter, int64_t* ranks, float* scores_out, void* workspace,
                     kge_stream_t stream) {
@@ -280,8 +289,8 @@ static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_ind
   p.ranks = reinterpret_cast<unsigned long long*>(ranks);
   p.scores_out = scores_out;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((Q + kTQ - 1) / kTQ), (unsigned)((p.N + kTE - 1) / kTE));
-  if (grid.y > 65535) return KGE_E_SIZE;
+  dim3 grid = fold_tiles((Q + kTQ - 1) / kTQ, (p.N + kTE - 1) / kTE);
+  if (grid.z > 65535) return KGE_E_SIZE;
   // dot-product models: GEMM on the tensor cores when the shape allows (otherwise the fp32 tiles);
   // the sharded variant keeps to the fp32 tiles (the tcgen05 kernel assumes row == entity id)
   const bool dot_model = !sh && (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT);
@@ -347,8 +356,8 @@ int dot_nt_launch(const float* a, const float* b, int64_t M, int64_t N, int Kd, 
   if (rank_tc_launch(a, b, N, Kd, p.queries, p.Q, nullptr, false, p.pos_score, p.seg, p.ranks, out, false, st) ==
       KGE_OK)
     return KGE_OK;
-  dim3 grid((unsigned)((M + kTQ - 1) / kTQ), (unsigned)((N + kTE - 1) / kTE));
-  if (grid.y > 65535) return KGE_E_SIZE;
+  dim3 grid = fold_tiles((M + kTQ - 1) / kTQ, (N + kTE - 1) / kTE);
+  if (grid.z > 65535) return KGE_E_SIZE;
   rank_tile_kernel<KGE_DISTMULT, false><<<grid, kThreads, 0, st>>>(p);
   KGE_LAUNCH_CHECK();
   return KGE_OK;

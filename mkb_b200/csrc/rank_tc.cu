@@ -143,7 +143,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_base = blockIdx.x * TC_M;
-  const int64_t e_base = (int64_t)blockIdx.y * TC_N;
+  const int64_t e_base = ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * TC_N;  // tiles folded over y, z
+  if (e_base >= p.N) return;  // the whole CTA, before any barrier / TMEM set-up
   const int num_kb = (p.Kd + TC_K - 1) / TC_K;
 
   if (warp == 0 && lane == 0) {
@@ -339,8 +340,8 @@ int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd
   p.head = head ? 1 : 0;
   cudaError_t e = cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)((Q + TC_M - 1) / TC_M), (unsigned)((n_entity + TC_N - 1) / TC_N));
-  if (grid.y > 65535) return KGE_E_UNSUPPORTED;
+  const int64_t e_tiles = (n_entity + TC_N - 1) / TC_N, ty = e_tiles < 32768 ? e_tiles : 32768;
+  dim3 grid((unsigned)((Q + TC_M - 1) / TC_M), (unsigned)ty, (unsigned)((e_tiles + ty - 1) / ty));
   rank_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mq, me, p);
   KGE_LAUNCH_CHECK();
   return KGE_OK;
