@@ -78,6 +78,12 @@ def _column_slices(D, parts, align=32):
 
 
 class DeviceTrainer:
+    COLSHARD_ABOVE_BYTES = 256 << 20  # entity-table size above which the default multi-GPU scheme is colshard
+
+    @staticmethod
+    def modulus_free(model):
+        return getattr(model, "kernel_modulus", None) is None  # pRotatE's trainable modulus: single-GPU flow only
+
     @classmethod
     def from_optimizer(cls, model, sampling, optimizer, alpha=0.5, max_batch=1024, **kw):
         """Adopt the hyper-parameters (and, if any, the moments) of a ``mkb_b200.optim.DenseAdam`` built
@@ -140,6 +146,12 @@ class DeviceTrainer:
             raise ValueError("virtual_shards is a single-process mode")
         if mode is None:
             mode = "rowshard" if self.virtual_shards else ("colpar" if self.distributed else "single")
+            # replicated tables cost one table all-gather over NVLink per step (colpar); above ~256 MB that
+            # dominates the step and the column-sharded scheme wins at every GPU count measured (DESIGN.md §6:
+            # config 4, 493 MB: 0.80 vs 1.30 ms/step on 4 GPUs; config 2, 116 MB: colpar 0.90 vs 0.94 on 8)
+            if (mode == "colpar" and ent.numel() * 4 > self.COLSHARD_ABOVE_BYTES and D % 4 == 0
+                    and D >= 32 * self.world and self.modulus_free(model)):
+                mode = "colshard"
         if mode == "colshard" and (not self.distributed or D % 4 != 0 or D < 32 * self.world):
             raise ValueError("colshard needs torch.distributed, hidden_dim % 4 == 0 and >= 32 columns per rank")
         if not self.distributed and mode != "rowshard":

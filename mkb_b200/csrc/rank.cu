@@ -47,6 +47,7 @@ struct RankParams {
   int has_filter;
   float* qmat;        // [Q][NC*D]
   float* pos_score;   // [Q]
+  float* posrows;     // [Q][NC*D] copy of every query's positive entity row (tensor-core path only, else null)
   int64_t* seg;       // [Q][2]
   unsigned long long* ranks;
   float* scores_out;  // optional [Q][N]
@@ -111,6 +112,11 @@ __global__ void __launch_bounds__(kThreads) rank_prepare_kernel(RankParams p) {
     make_query<M, HEAD>(a0, a1, r0, r1, q0, q1, p.phase_div);
     q[d] = q0;
     if constexpr (T::NC == 2) q[p.D + d] = q1;
+  }
+  if (p.posrows) {  // the tensor-core path re-scores the positive through the SAME GEMM as the candidates
+    const float* e = rk_entity_row(p, HEAD ? h : t);
+    float* dst = p.posrows + (int64_t)qi * p.ent_stride;
+    for (int d = threadIdx.x; d < p.ent_stride; d += blockDim.x) dst[d] = e[d];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -218,9 +224,14 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
 }
 
 // rank_tc.cu: tcgen05 (3xTF32) GEMM + fused rank count for the dot-product models
+// posrows (optional): [Q, kd] copy of every query's positive row; when given, a first small launch re-scores the
+// positives through the same tensor-core arithmetic and overwrites pos_score, so "s == s_pos" means what it means
+// in the reference (positive and candidates scored by one instruction sequence).
 int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
-                   const kge_filter_csr_t* filter, bool has_filter, const float* pos_score, const int64_t* seg,
-                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st);
+                   const kge_filter_csr_t* filter, bool has_filter, float* pos_score, const int64_t* seg,
+                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st,
+                   const float* posrows = nullptr);
+bool rank_tc_eligible(const float* ent, int kd, int64_t n_entity);
 
 }  // namespace kge
 
@@ -229,7 +240,8 @@ using namespace kge;
 extern "C" size_t kge_rank_workspace_bytes(const kge_tables_t* t, int64_t Q) {
   if (!t || Q <= 0) return 0;
   const size_t row = (size_t)t->hidden_dim * entity_comps(t->model);
-  return (size_t)Q * (row * sizeof(float) + sizeof(float) + 2 * sizeof(int64_t)) + 64;
+  const size_t pos = (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT) ? row * sizeof(float) : 0;  // posrows
+  return (size_t)Q * (row * sizeof(float) + sizeof(float) + 2 * sizeof(int64_t) + pos) + 64;
 }
 
 // (query tiles, entity tiles) -> grid: entity tiles beyond grid.y's 65 535 spill into grid.z
@@ -286,6 +298,7 @@ static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_ind
   p.qmat = reinterpret_cast<float*>(ws);
   ws += (size_t)Q * p.ent_stride * sizeof(float);
   p.pos_score = reinterpret_cast<float*>(ws);
+  ws += ((size_t)Q * sizeof(float) + 15) & ~(size_t)15;
   p.ranks = reinterpret_cast<unsigned long long*>(ranks);
   p.scores_out = scores_out;
   cudaStream_t st = (cudaStream_t)stream;
@@ -294,6 +307,7 @@ static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_ind
   // dot-product models: GEMM on the tensor cores when the shape allows (otherwise the fp32 tiles);
   // the sharded variant keeps to the fp32 tiles (the tcgen05 kernel assumes row == entity id)
   const bool dot_model = !sh && (t->model == KGE_COMPLEX || t->model == KGE_DISTMULT);
+  if (dot_model && rank_tc_eligible(p.ent, p.ent_stride, p.N)) p.posrows = reinterpret_cast<float*>(ws);
 #define KGE_CASE(MM)                                                                              \
   case MM:                                                                                        \
     if (mode == KGE_HEAD_BATCH) rank_prepare_kernel<MM, true><<<(unsigned)Q, kThreads, 0, st>>>(p); \
@@ -301,7 +315,7 @@ static int run_rank(const kge_tables_t* t, const kge_shards_t* sh, int shard_ind
     if (p.N == 0) break; /* a shard without rows (more shards than entities) */                   \
     if (dot_model &&                                                                              \
         rank_tc_launch(p.qmat, p.ent, p.N, p.ent_stride, queries, p.Q, filter, p.has_filter != 0, \
-                       p.pos_score, p.seg, p.ranks, scores_out, mode == KGE_HEAD_BATCH, st) == KGE_OK) \
+                       p.pos_score, p.seg, p.ranks, scores_out, mode == KGE_HEAD_BATCH, st, p.posrows) == KGE_OK) \
       break;                                                                                      \
     if (mode == KGE_HEAD_BATCH) rank_tile_kernel<MM, true><<<grid, kThreads, 0, st>>>(p);         \
     else rank_tile_kernel<MM, false><<<grid, kThreads, 0, st>>>(p);                               \

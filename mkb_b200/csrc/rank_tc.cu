@@ -38,6 +38,8 @@ struct RankTcParams {
   const int64_t* queries;
   kge_filter_csr_t filter;
   const float* pos_score;  // [Q]
+  float* pos_out;          // diag pass: where the re-scored positives go
+  int diag;                // 1: the "entity" operand is posrows [Q, Kd]; tile m only needs columns 128m .. 128m+127
   const int64_t* seg;      // [Q][2]
   unsigned long long* ranks;
   float* scores_out;
@@ -143,7 +145,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_base = blockIdx.x * TC_M;
-  const int64_t e_base = ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * TC_N;  // tiles folded over y, z
+  const int64_t e_base = p.diag ? (int64_t)(blockIdx.x >> 1) * TC_N  // the column tile holding this block's diagonal
+                                : ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * TC_N;  // folded over y, z
   if (e_base >= p.N) return;  // the whole CTA, before any barrier / TMEM set-up
   const int num_kb = (p.Kd + TC_K - 1) / TC_K;
 
@@ -259,7 +262,19 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       hi = p.seg[2 * qi + 1];
     }
     unsigned cnt = 0;
-    for (int c = 0; c < TC_N / 32; ++c) {
+    if (p.diag) {  // S[qi, qi]: the positive of query qi scored by the same MMAs as every candidate
+      const int col = qi - (int)e_base;
+      float s_diag = 0.f;
+      for (int c = 0; c < TC_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j == col) s_diag = __uint_as_float(v[j]);
+      }
+      if (vq) p.pos_out[qi] = s_diag;
+    }
+    for (int c = 0; c < (p.diag ? 0 : TC_N / 32); ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(c * 32), v);
       if (vq) {
@@ -316,17 +331,22 @@ static bool make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int
 
 // Returns KGE_OK when the tensor-core kernel was launched, KGE_E_UNSUPPORTED when the caller should use
 // the fp32 tile kernel instead (shape/alignment not eligible, or disabled with KGE_RANK_TC=0).
-int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
-                   const kge_filter_csr_t* filter, bool has_filter, const float* pos_score, const int64_t* seg,
-                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st) {
+bool rank_tc_eligible(const float* ent, int kd, int64_t n_entity) {
   if (const char* e = getenv("KGE_RANK_TC"))
-    if (atoi(e) == 0) return KGE_E_UNSUPPORTED;
-  if (kd % 4 != 0 || !aligned16(qmat) || !aligned16(ent) || n_entity > INT32_MAX) return KGE_E_UNSUPPORTED;
+    if (atoi(e) == 0) return false;
   static EncodeTiledFn enc = encode_fn();
-  if (!enc) return KGE_E_UNSUPPORTED;
-  CUtensorMap mq, me;
+  return enc && kd % 4 == 0 && aligned16(ent) && n_entity <= INT32_MAX;
+}
+
+int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
+                   const kge_filter_csr_t* filter, bool has_filter, float* pos_score, const int64_t* seg,
+                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st, const float* posrows) {
+  if (!rank_tc_eligible(ent, kd, n_entity) || !aligned16(qmat)) return KGE_E_UNSUPPORTED;
+  static EncodeTiledFn enc = encode_fn();
+  CUtensorMap mq, me, mp;
   if (!make_map(enc, &mq, qmat, Q, kd, TC_M) || !make_map(enc, &me, ent, n_entity, kd, TC_N))
     return KGE_E_UNSUPPORTED;
+  if (posrows && (!aligned16(posrows) || !make_map(enc, &mp, posrows, Q, kd, TC_N))) return KGE_E_UNSUPPORTED;
   RankTcParams p{};
   p.queries = queries;
   if (has_filter) p.filter = *filter;
@@ -340,6 +360,14 @@ int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd
   p.head = head ? 1 : 0;
   cudaError_t e = cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
+  if (posrows) {  // diag pass: positives re-scored by the tensor cores, one CTA per 128 queries
+    RankTcParams pd = p;
+    pd.diag = 1;
+    pd.N = Q;
+    pd.pos_out = pos_score;
+    rank_tc_kernel<<<dim3((unsigned)((Q + TC_M - 1) / TC_M)), 256, TC_SMEM_BYTES, st>>>(mq, mp, pd);
+    KGE_LAUNCH_CHECK();
+  }
   const int64_t e_tiles = (n_entity + TC_N - 1) / TC_N, ty = e_tiles < 32768 ? e_tiles : 32768;
   dim3 grid((unsigned)((Q + TC_M - 1) / TC_M), (unsigned)ty, (unsigned)((e_tiles + ty - 1) / ty));
   rank_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mq, me, p);

@@ -191,9 +191,10 @@ STUB = """// rank_tc.cu (tcgen05 / TMA) is not emulated: report "unsupported" so
 #include "kge_common.cuh"
 namespace kge {
 int rank_tc_launch(const float*, const float*, int64_t, int, const int64_t*, int, const kge_filter_csr_t*, bool,
-                   const float*, const int64_t*, unsigned long long*, float*, bool, cudaStream_t) {
+                   float*, const int64_t*, unsigned long long*, float*, bool, cudaStream_t, const float*) {
   return KGE_E_UNSUPPORTED;
 }
+bool rank_tc_eligible(const float*, int, int64_t) { return false; }
 }  // namespace kge
 extern "C" long kge_emu_launch_count(void) { return emu::S.launches; }
 """

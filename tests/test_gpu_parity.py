@@ -550,3 +550,32 @@ def test_multi_record_backward_equals_per_record_launches():
     assert g2.abs().max().item() > 0
     assert (g1 - g2).abs().max().item() <= 1e-5 * g2.abs().max().item()
     assert (r1 - r2).abs().max().item() <= 1e-5 * r2.abs().max().item()
+
+
+@pytest.mark.parametrize("model", ("ComplEx", "DistMult", "RotatE"))
+def test_rank_exact_ties_resolve_by_entity_id(model):
+    """Duplicate entity rows score EXACTLY like the positive; the reference's (stable) descending sort puts the copies
+    with a smaller id ahead of the positive and the others behind it.  On the tensor-core path this only holds when
+    the positive is scored by the same GEMM as the candidates (rank_tc's diag pass)."""
+    rng = np.random.RandomState(21)
+    Nn, R, D, Q = 700, 4, 64, 48  # several 256-entity tiles
+    ent, rel = ko.init_tables(model, Nn, R, D, 9.0, seed=8)
+    ent *= 3
+    tri = np.unique(np.stack([rng.randint(5, Nn - 5, size=2500), rng.randint(R, size=2500), rng.randint(5, Nn - 5, size=2500)], 1), axis=0)
+    queries = tri[rng.choice(len(tri), Q, replace=False)]
+    pos = np.unique(queries[:, 2])
+    taken = set(pos.tolist())
+    expect_extra = np.zeros(Q, dtype=np.int64)
+    for k, t in enumerate(pos[:12]):  # copies of the positive's row just below and just above its id
+        for nb in (t - 1, t + 1, t - 2):
+            if nb not in taken:
+                ent[nb] = ent[t]
+                taken.add(nb)
+    hc, tc = ko.build_filter_csr(tri, Nn, "head"), ko.build_filter_csr(tri, Nn, "tail")
+    m = _model(model, ent, rel, 9.0)
+    ev = evaluation.Evaluation(entities={i: i for i in range(Nn)}, relations={i: i for i in range(R)}, batch_size=8,
+                               true_triples=[tuple(map(int, r)) for r in tri])
+    ref, contested = ko.rank_all(model, ent, rel, queries, "tail-batch", hc, tc, gamma=9.0, tie_margin=1e-9)
+    assert contested.max() >= 1  # the construction produced exact ties the oracle sees
+    got = ev.ranks(m, [tuple(map(int, r)) for r in queries], "tail-batch").cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
