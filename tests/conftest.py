@@ -28,7 +28,7 @@ def pytest_configure(config):
 # Order of the `-m gpu` run: the files whose kernels have B200 measurements behind them first, the rows
 # written after the round's GPU budget was spent next, the tcgen05 pooled-GEMM flow (spin-waits on mbarriers)
 # last — so `-x` reports as much as possible before the least-exercised code runs.
-_GPU_FILE_ORDER = ("test_gpu_parity", "test_gpu_advice", "test_gpu_fullshape", "test_gpu_cfg5", "test_gpu_multi",
+_GPU_FILE_ORDER = ("test_gpu_parity", "test_gpu_advice", "test_gpu_fullshape", "test_gpu_cfg5", "test_gpu_cfg1_epoch", "test_gpu_multi",
                    "test_gpu_rows_next", "test_gpu_sharded", "test_gpu_train_byent")
 
 

@@ -726,8 +726,66 @@ def gen_cfg5_cases(n_queries=64, n_queries_rotate=32):
     print("cfg5_wn18rr", len(out))
 
 
+def gen_cfg1_epoch():
+    """BASELINE config 1 exactly as worded — "Wn18rr TransE dim=200 batch=256 neg=64 Adversarial loss on CPU
+    (reference compose.Pipeline, 1 epoch)" — run through the UNMODIFIED reference: mkb.datasets.Wn18rr,
+    models.TransE, sampling.NegativeSampling, losses.Adversarial, torch.optim.Adam, compose.Pipeline(epochs=1).learn
+    (compose/pipeline.py:202-244).  Stored: the loss of every step (recorded by wrapping the loss object), the
+    trained relation table, 512 sampled rows of the trained entity table + a checksum of the whole table, and the
+    seeds — so the CUDA path can replay the epoch (same loader order, same reference-pool negatives) and must land
+    on the same trajectory."""
+    from mkb import compose
+
+    out = {}
+    D, B, K, gamma, lr, seed = 200, 256, 64, 6.0, 5e-5, 42
+    torch.manual_seed(seed)
+    ds = datasets.Wn18rr(batch_size=B, shuffle=True, seed=seed)
+    model = models.TransE(hidden_dim=D, entities=ds.entities, relations=ds.relations, gamma=gamma)
+    out["ent0_checksum"] = np.float64(_np(model.entity_embedding).astype(np.float64).sum())
+    sampler = sampling.NegativeSampling(size=K, train_triples=ds.train, entities=ds.entities, relations=ds.relations,
+                                        seed=seed)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=lr)
+    base = losses.Adversarial(alpha=0.5)
+    seen = []
+
+    def rec_loss(positive_score, negative_score, weight):
+        err = base(positive_score, negative_score, weight)
+        seen.append(float(err.detach()))
+        return err
+
+    import time as _t
+    t0 = _t.time()
+    pipe = compose.Pipeline(epochs=1)
+    old = sys.stdout
+    sys.stdout = open(os.devnull, "w")
+    try:
+        class _NoEval:  # the reference dereferences `evaluation` unguarded after the last epoch (SURVEY App. B.12)
+            def eval(self, model, dataset):
+                return {}
+
+            def eval_relations(self, model, dataset):
+                return {}
+
+        pipe.learn(model=model, dataset=ds, sampling=sampler, optimizer=opt, loss=rec_loss, evaluation=_NoEval())
+    finally:
+        sys.stdout = old
+    ent, rel = _np(model.entity_embedding), _np(model.relation_embedding)
+    rows = np.random.RandomState(7).choice(ent.shape[0], 512, replace=False)
+    out.update({"hidden_dim": np.int64(D), "batch": np.int64(B), "neg": np.int64(K), "gamma": np.float64(gamma),
+                "lr": np.float64(lr), "seed": np.int64(seed), "losses": np.array(seen, dtype=np.float64),
+                "rel_final": rel, "rows": rows.astype(np.int64), "ent_rows_final": ent[rows],
+                "ent_checksum": np.float64(ent.astype(np.float64).sum()),
+                "ent_abs_checksum": np.float64(np.abs(ent).astype(np.float64).sum()),
+                "rolling_loss": np.float64(pipe.metric_loss.get())})
+    np.savez_compressed(os.path.join(HERE, "cfg1_epoch.npz"), **out)
+    print("cfg1_epoch", len(seen), "steps in", f"{_t.time() - t0:.0f}s; loss", seen[0], "->", seen[-1])
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["step", "pins", "sampler", "eval", "evaldoc", "loader", "next", "distill", "distilldoc"]
+    if "cfg1" in which:  # ~1-2 min of CPU: one reference epoch of config 1
+        gen_cfg1_epoch()
+        sys.exit(0)
     if "cfg5" in which:  # ~20 min of CPU (the reference ranks 40 943 candidates x D=1000 per query)
         gen_cfg5_cases(*[int(a) for a in which[which.index("cfg5") + 1:][:2]])
         sys.exit(0)

@@ -147,3 +147,57 @@ def test_two_gpu_trainer_matches_single_gpu(mode, packed, handshake):
     assert out["loss"] < 1e-5
     # 4 Adam steps of lr 1e-3 move parameters by ~4e-3; replicas must agree with the replay to ~1e-6
     assert out["ent"] < 2e-5 and out["rel"] < 2e-5
+
+
+def _worker_pipeline(rank, world, port, out, mode):
+    """compose.Pipeline.learn under torch.distributed: every batch of the Dataset is the GLOBAL batch, rank r trains on
+    its r-th block with its own negative stream; replicas / gathered shards end up identical on all
+    ranks and the loss falls."""
+    import torch.distributed as dist
+
+    from mkb_b200 import compose, datasets, losses, models, optim, sampling
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    Nn, R, D, B, K = 2000, 7, 128, 130, 16  # 130: not a multiple of world * anything -> padded blocks
+    rng = np.random.RandomState(0)
+    tri = sorted({(int(rng.randint(Nn)), int(rng.randint(R)), int(rng.randint(Nn))) for _ in range(6000)})
+    ents, rels = {i: i for i in range(Nn)}, {i: i for i in range(R)}
+    ds = datasets.Dataset(train=tri, entities=ents, relations=rels, batch_size=B, shuffle=True, seed=42)
+    torch.manual_seed(3)
+    m = models.RotatE(hidden_dim=D, entities=ents, relations=rels, gamma=9.0).to(dev)
+    ns = sampling.NegativeSampling(size=K, train_triples=tri, entities=ents, relations=rels, seed=5)
+    opt = optim.DenseAdam([p for p in m.parameters() if p.requires_grad], lr=5e-3)
+    pipe = compose.Pipeline(epochs=1, device=dev, trainer_options={"mode": mode})
+    pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
+    first = pipe.metric_loss.get()
+    pipe.epochs = 3  # the same Pipeline keeps its DeviceTrainer (moments, shards) across learn() calls
+    pipe.learn(model=m, dataset=ds, sampling=ns, optimizer=opt, loss=losses.Adversarial(0.5))
+    tr = pipe._trainer
+    gathered = [torch.empty_like(m.entity_embedding.data) for _ in range(world)]
+    dist.all_gather(gathered, m.entity_embedding.data.contiguous())
+    diff = max((g - gathered[0]).abs().max().item() for g in gathered)
+    if rank == 0:
+        out.update(mode=tr.mode, per_rank_batch=tr.max_batch, first=first, last=pipe.metric_loss.get(), diff=diff,
+                   steps=tr.t, expected_steps=4 * 2 * -(-len(tri) // B))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ("colpar", "colshard", "allreduce"))
+def test_two_gpu_pipeline_learn(mode):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_worker_pipeline, args=(2, port, out, mode), nprocs=2, join=True)
+    print(dict(out))
+    assert out["mode"] == mode and out["per_rank_batch"] == 65 and out["steps"] == out["expected_steps"]
+    assert out["diff"] == 0.0  # every rank holds the same table after training
+    assert out["last"] < out["first"] - 0.02
