@@ -321,6 +321,9 @@ class DeviceTrainer:
     def _setup_colshard(self, model, f32):
         import torch.distributed._symmetric_memory as symm
 
+        # blocks of the global batch travel in 16-byte units: the per-rank batch is rounded up to a multiple of 4
+        # (short batches are padded with weight-0 rows anyway)
+        self.max_batch = (self.max_batch + 3) // 4 * 4
         G, r, B, K = self.world, self.rank, self.max_batch, self.K
         self.col0, self.ncols = _column_slices(self.D, G)[r]
         w = self.ncols
