@@ -16,6 +16,8 @@
 // Bound: RotatE is MUFU-bound (one sqrt per query x entity x dim), TransE FP32-bound, the two
 // dot-product models FP32-FMA-bound in this fp32 formulation (tensor-core split-bf16 is a later
 // row); none is HBM-bound: the entity table is re-read once per 64 queries out of L2.
+#include <cstdlib>
+
 #include "kge_common.cuh"
 
 namespace kge {
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
 int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
                    const kge_filter_csr_t* filter, bool has_filter, float* pos_score, const int64_t* seg,
                    unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st,
-                   const float* posrows = nullptr);
+                   const float* posrows = nullptr, int k_split = 1);
 bool rank_tc_eligible(const float* ent, int kd, int64_t n_entity);
 
 }  // namespace kge
@@ -367,8 +369,20 @@ int dot_nt_launch(const float* a, const float* b, int64_t M, int64_t N, int Kd, 
   p.D = Kd;
   p.ent_stride = Kd;
   p.scores_out = out;
-  if (rank_tc_launch(a, b, N, Kd, p.queries, p.Q, nullptr, false, p.pos_score, p.seg, p.ranks, out, false, st) ==
-      KGE_OK)
+  // small M x N (the pooled flow's 1024 x 512 x 2000 GEMMs are 16-64 tiles for 148 SMs): split K over grid.z so
+  // that ~one wave of CTAs is busy; partial sums are added into `out` (zeroed here).  KGE_DOT_SPLITK=0: off.
+  int k_split = 1;
+  if (rank_tc_eligible(b, Kd, N) && aligned16(a)) {
+    const int64_t tiles = ((M + 127) / 128) * ((N + 255) / 256);
+    const char* env = getenv("KGE_DOT_SPLITK");
+    if (tiles < 96 && !(env && atoi(env) == 0)) {
+      k_split = (int)(148 / tiles);
+      if (k_split > (Kd + 31) / 32) k_split = (Kd + 31) / 32;
+      if (k_split > 1 && cudaMemsetAsync(out, 0, (size_t)M * N * sizeof(float), st) != cudaSuccess) k_split = 1;
+    }
+  }
+  if (rank_tc_launch(a, b, N, Kd, p.queries, p.Q, nullptr, false, p.pos_score, p.seg, p.ranks, out, false, st, nullptr,
+                     k_split) == KGE_OK)
     return KGE_OK;
   dim3 grid = fold_tiles((M + kTQ - 1) / kTQ, (N + kTE - 1) / kTE);
   if (grid.z > 65535) return KGE_E_SIZE;

@@ -40,6 +40,8 @@ struct RankTcParams {
   const float* pos_score;  // [Q]
   float* pos_out;          // diag pass: where the re-scored positives go
   int diag;                // 1: the "entity" operand is posrows [Q, Kd]; tile m only needs columns 128m .. 128m+127
+  int k_split;             // > 1 (plain GEMM use only): blockIdx.z owns kb_per_split k-blocks, results are ADDED into
+  int kb_per_split;        //     scores_out with fp32 REDs (the caller zeroes it) — fills the SMs when M x N is small
   const int64_t* seg;      // [Q][2]
   unsigned long long* ranks;
   float* scores_out;
@@ -145,10 +147,14 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_base = blockIdx.x * TC_M;
+  const bool ksplit = p.k_split > 1;
   const int64_t e_base = p.diag ? (int64_t)(blockIdx.x >> 1) * TC_N  // the column tile holding this block's diagonal
-                                : ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * TC_N;  // folded over y, z
+                         : ksplit ? (int64_t)blockIdx.y * TC_N       // grid.z is the k-split index
+                                 : ((int64_t)blockIdx.y + (int64_t)blockIdx.z * gridDim.y) * TC_N;  // folded over y, z
   if (e_base >= p.N) return;  // the whole CTA, before any barrier / TMEM set-up
-  const int num_kb = (p.Kd + TC_K - 1) / TC_K;
+  const int all_kb = (p.Kd + TC_K - 1) / TC_K;
+  const int kb0 = ksplit ? (int)blockIdx.z * p.kb_per_split : 0;  // this CTA's k-blocks: [kb0, kb0 + num_kb)
+  const int num_kb = ksplit ? min(p.kb_per_split, all_kb - kb0) : all_kb;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -182,8 +188,8 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (kb >= TC_STAGES) mbar_wait(&empty[s], ((kb / TC_STAGES) - 1) & 1);
         uint8_t* st = smem + s * TC_STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], TC_A_BYTES + TC_B_BYTES);
-        tma_load_2d(st, &map_q, &full[s], kb * TC_K, q_base);
-        tma_load_2d(st + 2 * TC_A_BYTES, &map_e, &full[s], kb * TC_K, (int)e_base);
+        tma_load_2d(st, &map_q, &full[s], (kb0 + kb) * TC_K, q_base);
+        tma_load_2d(st + 2 * TC_A_BYTES, &map_e, &full[s], (kb0 + kb) * TC_K, (int)e_base);
       }
     }
   } else if (warp == 1) {
@@ -287,7 +293,11 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             bool filtered = false;
             if ((beats || p.scores_out) && e != pos && hi > lo) filtered = tc_member(p.filter.members, lo, hi, e);
             if (beats && e != pos && !filtered) ++cnt;
-            if (p.scores_out) p.scores_out[(int64_t)qi * p.N + e] = filtered ? sp + (-1e5f) : (e == pos ? sp : s);
+            if (p.scores_out) {
+              float* dst = p.scores_out + (int64_t)qi * p.N + e;
+              if (ksplit) atomicAdd(dst, s);  // partial sum of this k-split (RED.ADD.F32; plain-GEMM use: no filter)
+              else *dst = filtered ? sp + (-1e5f) : (e == pos ? sp : s);
+            }
           }
         }
       }
@@ -340,7 +350,8 @@ bool rank_tc_eligible(const float* ent, int kd, int64_t n_entity) {
 
 int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd, const int64_t* queries, int Q,
                    const kge_filter_csr_t* filter, bool has_filter, float* pos_score, const int64_t* seg,
-                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st, const float* posrows) {
+                   unsigned long long* ranks, float* scores_out, bool head, cudaStream_t st, const float* posrows,
+                   int k_split) {
   if (!rank_tc_eligible(ent, kd, n_entity) || !aligned16(qmat)) return KGE_E_UNSUPPORTED;
   static EncodeTiledFn enc = encode_fn();
   CUtensorMap mq, me, mp;
@@ -370,6 +381,13 @@ int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd
   }
   const int64_t e_tiles = (n_entity + TC_N - 1) / TC_N, ty = e_tiles < 32768 ? e_tiles : 32768;
   dim3 grid((unsigned)((Q + TC_M - 1) / TC_M), (unsigned)ty, (unsigned)((e_tiles + ty - 1) / ty));
+  if (k_split > 1 && scores_out && !posrows && grid.z == 1) {  // split-K: the caller has zeroed scores_out
+    const int all_kb = (kd + TC_K - 1) / TC_K;
+    p.kb_per_split = (all_kb + k_split - 1) / k_split;
+    p.k_split = (all_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    if (p.k_split > 1) grid.z = (unsigned)p.k_split;
+    else p.k_split = 0;
+  }
   rank_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mq, me, p);
   KGE_LAUNCH_CHECK();
   return KGE_OK;

@@ -191,7 +191,7 @@ STUB = """// rank_tc.cu (tcgen05 / TMA) is not emulated: report "unsupported" so
 #include "kge_common.cuh"
 namespace kge {
 int rank_tc_launch(const float*, const float*, int64_t, int, const int64_t*, int, const kge_filter_csr_t*, bool,
-                   float*, const int64_t*, unsigned long long*, float*, bool, cudaStream_t, const float*) {
+                   float*, const int64_t*, unsigned long long*, float*, bool, cudaStream_t, const float*, int) {
   return KGE_E_UNSUPPORTED;
 }
 bool rank_tc_eligible(const float*, int, int64_t) { return false; }
