@@ -280,25 +280,72 @@ rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       if (vq) p.pos_out[qi] = s_diag;
     }
-    for (int c = 0; c < (p.diag ? 0 : TC_N / 32); ++c) {
+    // Ranking without a score dump: per 32-column chunk a bit mask of the candidates that beat the positive, from
+    // which the FILTERED ones are cleared by walking this query's (sorted) filter segment once across the tile —
+    // one lower_bound per tile and thread instead of one binary search per beating candidate (with untrained
+    // tables half of all candidates beat the positive: ~100 us of dependent L2 loads per tile, more than the MMAs).
+    int64_t cur = lo;
+    if (!p.diag && !p.scores_out && vq && hi > lo) {
+      int64_t a = lo, b = hi;
+      while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (__ldg(p.filter.members + mid) < e_base) a = mid + 1;
+        else b = mid;
+      }
+      cur = a;
+    }
+    for (int c = 0; c < ((p.diag || p.scores_out) ? 0 : TC_N / 32); ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(c * 32), v);
       if (vq) {
+        const int64_t c0 = e_base + c * 32;
+        unsigned beats = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int64_t e = e_base + c * 32 + j;
-          if (e < p.N) {
-            const float s = __uint_as_float(v[j]);
-            const bool beats = (s > sp) || (s == sp && e < pos);
-            bool filtered = false;
-            if ((beats || p.scores_out) && e != pos && hi > lo) filtered = tc_member(p.filter.members, lo, hi, e);
-            if (beats && e != pos && !filtered) ++cnt;
-            if (p.scores_out) {
-              float* dst = p.scores_out + (int64_t)qi * p.N + e;
-              if (ksplit) atomicAdd(dst, s);  // partial sum of this k-split (RED.ADD.F32; plain-GEMM use: no filter)
-              else *dst = filtered ? sp + (-1e5f) : (e == pos ? sp : s);
-            }
-          }
+          const int64_t e = c0 + j;
+          const float s = __uint_as_float(v[j]);
+          if (e < p.N && e != pos && ((s > sp) || (s == sp && e < pos))) beats |= 1u << j;
+        }
+        while (cur < hi) {  // filtered entities inside this chunk never count
+          const int64_t m = __ldg(p.filter.members + cur);
+          if (m >= c0 + 32) break;
+          beats &= ~(1u << (int)(m - c0));
+          ++cur;
+        }
+        cnt += __popc(beats);
+      }
+    }
+    // With a score dump: element by element, and the 32 x 32 block of every chunk goes through shared memory so that
+    // the global stores (or, with split-K, the fp32 REDs) of a warp are 128-byte rows instead of 32 scattered words
+    // (the stage buffers are free: tmem_full says every MMA has finished reading them).
+    float* tbuf = reinterpret_cast<float*>(smem) + w4 * (32 * 33);
+    for (int c = 0; c < ((p.diag || !p.scores_out) ? 0 : TC_N / 32); ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(c * 32), v);
+      __syncwarp();  // the previous chunk's reads of tbuf are done
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t e = e_base + c * 32 + j;
+        float outv = 0.f;
+        if (vq && e < p.N) {
+          const float s = __uint_as_float(v[j]);
+          const bool beats = (s > sp) || (s == sp && e < pos);
+          bool filtered = false;
+          if (e != pos && hi > lo) filtered = tc_member(p.filter.members, lo, hi, e);
+          if (beats && e != pos && !filtered) ++cnt;
+          outv = ksplit ? s : (filtered ? sp + (-1e5f) : (e == pos ? sp : s));
+        }
+        tbuf[lane * 33 + j] = outv;
+      }
+      __syncwarp();
+      const int64_t e = e_base + c * 32 + lane;  // lane = column now
+      if (e < p.N) {
+        for (int r = 0; r < 32; ++r) {
+          const int qr = q_base + w4 * 32 + r;
+          if (qr >= p.Q) break;
+          float* dst = p.scores_out + (int64_t)qr * p.N + e;
+          if (ksplit) atomicAdd(dst, tbuf[r * 33 + lane]);  // partial sum of this k-split (RED.ADD.F32)
+          else *dst = tbuf[r * 33 + lane];
         }
       }
     }
