@@ -137,3 +137,20 @@ def test_distributed_evaluation_restores_query_order():
     assert all(n in (11, 12) for n in out["seen"])  # each rank only ranked its slice
     both = np.concatenate([out["ref"]["head-batch"], out["ref"]["tail-batch"]])
     assert out["metrics"] == ko.rank_metrics(both)
+
+
+def test_weight_zero_padding_rows_change_nothing():
+    """compose.Pipeline._rank_slice and DeviceTrainer's colshard step pad short per-rank batches with copies of row 0
+    at weight 0.  In the reference's loss every term of a positive carries its weight (losses/adversarial.py:22-30),
+    so such rows must leave the loss and every gradient untouched — checked on the oracle's closed forms."""
+    ent, rel, sample, neg, w = _problem()
+    s, n, ww = sample[:B], neg[:B], w[:B]
+    ref = ko.train_step(MODEL, ent, rel, s, n, "tail-batch", ww, gamma=GAMMA)
+    pad = 5
+    s2 = np.concatenate([s, np.repeat(s[:1], pad, axis=0)])
+    n2 = np.concatenate([n, np.repeat(n[:1], pad, axis=0)])
+    w2 = np.concatenate([ww, np.zeros(pad)])
+    got = ko.train_step(MODEL, ent, rel, s2, n2, "tail-batch", w2, gamma=GAMMA)
+    assert abs(got[0] - ref[0]) <= 1e-12 * abs(ref[0])  # loss
+    np.testing.assert_allclose(got[3], ref[3], rtol=0, atol=1e-15)  # entity gradient
+    np.testing.assert_allclose(got[4], ref[4], rtol=0, atol=1e-15)  # relation gradient
