@@ -199,6 +199,38 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
     const int qi = q_base + ty * 4 + a;
     const bool vq = qi < p.Q;  // uniform over the 16 threads that share ty
     unsigned cnt = 0;
+    // Which of this tile's 64 entities are filtered for query qi: ONE thread of the half-warp that shares the query
+    // walks the query's (sorted) filter segment across the tile's id span and broadcasts a 64-bit mask — one
+    // lower_bound per query and tile instead of a binary search per beating candidate (with untrained tables half
+    // of all candidates beat the positive).  The score-dump path keeps the per-element lookup.
+    unsigned long long fmask = 0ull;
+    if (!p.scores_out) {
+      unsigned m_lo = 0u, m_hi = 0u;
+      if (vq && tx == 0) {
+        const int64_t lo = p.seg[2 * qi], hi = p.seg[2 * qi + 1];
+        if (hi > lo) {
+          const int64_t last_row = (e_base + kTE - 1 < p.N ? e_base + kTE - 1 : p.N - 1);
+          const int64_t first = e_base * p.id_mul + p.id_add, last = last_row * p.id_mul + p.id_add;
+          int64_t a0 = lo, b0 = hi;
+          while (a0 < b0) {
+            const int64_t mid = (a0 + b0) >> 1;
+            if (__ldg(p.filter.members + mid) < first) a0 = mid + 1;
+            else b0 = mid;
+          }
+          for (int64_t k = a0; k < hi; ++k) {
+            const int64_t m = __ldg(p.filter.members + k);
+            if (m > last) break;
+            const int64_t r = m - p.id_add;
+            if (r % p.id_mul == 0) fmask |= 1ull << (int)(r / p.id_mul - e_base);
+          }
+        }
+        m_lo = (unsigned)fmask;
+        m_hi = (unsigned)(fmask >> 32);
+      }
+      m_lo = __shfl_sync(kFull, m_lo, lane & 16);  // lane 0 / 16 = tx 0 of this half-warp
+      m_hi = __shfl_sync(kFull, m_hi, lane & 16);
+      fmask = ((unsigned long long)m_hi << 32) | m_lo;
+    }
     if (vq) {
       const float sp = p.pos_score[qi];
       const int64_t pos = p.queries[3 * qi + (HEAD ? 0 : 2)];
@@ -210,9 +242,8 @@ __global__ void __launch_bounds__(kThreads) rank_tile_kernel(RankParams p) {
           const int64_t e = el * p.id_mul + p.id_add;
           const float s = finish_score<M>(acc[a][b], p.gamma, rk_modulus<M>(p));
           const bool beats = (s > sp) || (s == sp && e < pos);
-          bool filtered = false;
-          if ((beats || p.scores_out) && e != pos && hi > lo)
-            filtered = rk_member(p.filter.members, lo, hi, e);
+          bool filtered = (fmask >> (tx * 4 + b)) & 1ull;
+          if (p.scores_out && e != pos && hi > lo) filtered = rk_member(p.filter.members, lo, hi, e);
           if (beats && e != pos && !filtered) ++cnt;
           if (p.scores_out) p.scores_out[(int64_t)qi * p.n_global + e] = filtered ? sp + (-1e5f) : s;
         }
