@@ -28,11 +28,11 @@
 
 namespace kge {
 
-constexpr int TC_M = 128, TC_N = 256, TC_K = 32, TC_STAGES = 2;
+constexpr int TC_M = 128, TC_N = 256, TC_K = 32;
 constexpr int TC_A_BYTES = TC_M * TC_K * 4;  // 16 KB
 constexpr int TC_B_BYTES = TC_N * TC_K * 4;  // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // A, A_lo, B, B_lo = 96 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct RankTcParams {
   const int64_t* queries;
@@ -133,7 +133,11 @@ __device__ __forceinline__ bool tc_member(const int64_t* __restrict__ m, int64_t
   return false;
 }
 
-__global__ void __launch_bounds__(256, 1)
+// TC_STAGES = 2, one CTA per SM (192 KB): the measured default.  TC_STAGES = 1 with TWO CTAs per SM (2 x 96 KB of
+// shared memory, 2 x 256 TMEM columns): each CTA runs TMA -> split -> MMA serially, the pair interleaves on the SM's
+// tensor pipe, and one CTA's prologue / epilogue overlaps the other's main loop (A/B: KGE_TC_STAGES=1).
+template <int TC_STAGES>
+__global__ void __launch_bounds__(256, TC_STAGES == 1 ? 2 : 1)
 rank_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_e,
                RankTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -416,14 +420,17 @@ int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd
   p.Q = Q;
   p.Kd = kd;
   p.head = head ? 1 : 0;
-  cudaError_t e = cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  static const int stages = (getenv("KGE_TC_STAGES") && atoi(getenv("KGE_TC_STAGES")) == 1) ? 1 : 2;
+  auto kern = stages == 1 ? rank_tc_kernel<1> : rank_tc_kernel<2>;
+  const int smem_bytes = tc_smem_bytes(stages);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return (int)e;
   if (posrows) {  // diag pass: positives re-scored by the tensor cores, one CTA per 128 queries
     RankTcParams pd = p;
     pd.diag = 1;
     pd.N = Q;
     pd.pos_out = pos_score;
-    rank_tc_kernel<<<dim3((unsigned)((Q + TC_M - 1) / TC_M)), 256, TC_SMEM_BYTES, st>>>(mq, mp, pd);
+    kern<<<dim3((unsigned)((Q + TC_M - 1) / TC_M)), 256, smem_bytes, st>>>(mq, mp, pd);
     KGE_LAUNCH_CHECK();
   }
   const int64_t e_tiles = (n_entity + TC_N - 1) / TC_N, ty = e_tiles < 32768 ? e_tiles : 32768;
@@ -435,7 +442,7 @@ int rank_tc_launch(const float* qmat, const float* ent, int64_t n_entity, int kd
     if (p.k_split > 1) grid.z = (unsigned)p.k_split;
     else p.k_split = 0;
   }
-  rank_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(mq, me, p);
+  kern<<<grid, 256, smem_bytes, st>>>(mq, me, p);
   KGE_LAUNCH_CHECK();
   return KGE_OK;
 }
