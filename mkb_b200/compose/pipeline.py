@@ -42,6 +42,8 @@ class _RollingMean:
 
 
 class Pipeline:
+    LOSS_LAG = 3  # device-resident route: the loss of step k is read back (and logged) after step k + LOSS_LAG was queued
+
     def __init__(self, epochs, eval_every=2000, early_stopping_rounds=3, device="cpu", fused=True,
                  loss_every=1, trainer_options=None, adopt_torch_adam=True):
         """``fused=False`` forces the generic three-call loop.  ``loss_every`` > 1 reads the loss back
@@ -139,11 +141,13 @@ class Pipeline:
     def _learn_on_device(self, trainer, dataset, epoch, optimizer=None):
         """Device-resident epoch: per batch two async H2D copies (skipped when the dataset already
         lives on the GPU), five kernel launches, and an async D2H copy of the loss sums into pinned
-        memory that is read one step later (the reference's ``error.item()`` without the stall)."""
+        memory that is read ``LOSS_LAG`` steps later (the reference's ``error.item()`` without the stall: the host
+        may run a few steps ahead of the device, which absorbs its own jitter — the data loader, tqdm, the GC)."""
         dev = trainer.dev
-        host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
-        pending = None
+        depth = self.LOSS_LAG + 1
+        host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        done = [torch.cuda.Event() for _ in range(depth)]
+        pending = collections.deque()
         if optimizer is not None:
             trainer.adopt_hyper_parameters(optimizer)
         bar = Bar(dataset=dataset, update_every=10)
@@ -154,13 +158,14 @@ class Pipeline:
             sample = sample.to(dev, non_blocking=True)
             weight = weight.to(dev, non_blocking=True)
             stats = trainer.step(sample, weight, data["mode"])
-            host[k & 1].copy_(stats, non_blocking=True)
-            done[k & 1].record()
-            if pending is not None:
-                self._record_loss(pending, host, done, bar, epoch)
-            pending = k & 1
-        if pending is not None:
-            self._record_loss(pending, host, done, bar, epoch)
+            slot = k % depth
+            host[slot].copy_(stats, non_blocking=True)
+            done[slot].record()
+            pending.append(slot)
+            if len(pending) == depth:  # the slot the NEXT step will overwrite must have been read
+                self._record_loss(pending.popleft(), host, done, bar, epoch)
+        while pending:
+            self._record_loss(pending.popleft(), host, done, bar, epoch)
         trainer.sync_optimizer_state()
         trainer.sync_model()  # rowshard: gather the trained shards back into model.entity_embedding
 
