@@ -154,3 +154,57 @@ def test_weight_zero_padding_rows_change_nothing():
     assert abs(got[0] - ref[0]) <= 1e-12 * abs(ref[0])  # loss
     np.testing.assert_allclose(got[3], ref[3], rtol=0, atol=1e-15)  # entity gradient
     np.testing.assert_allclose(got[4], ref[4], rtol=0, atol=1e-15)  # relation gradient
+
+
+def _colshard_worker(rank, world, port, out, model):
+    """The exchange pattern of DeviceTrainer(mode="colshard") under a real process group (gloo): rank r holds the
+    hidden-dim columns slice r of every row, scores the GLOBAL batch over its columns, ONE all-reduce sums the partial
+    scores, every rank forms the per-score gradients redundantly and differentiates its own sub-table.  Per-rank
+    arithmetic: the oracle's (the kernels' version of the same algebra is tested on the emulation,
+    test_column_sharded_step_equals_the_full_step).  TransE covers the "(G-1) * gamma" correction of the distance
+    models, ComplEx the plain sum of the dot-product ones (both have no hidden-dim-dependent constant)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(3)
+    ent, rel = ko.init_tables(model, N, R, D, GAMMA, seed=5)
+    ent, rel = ent.astype(np.float64) * 3, rel.astype(np.float64)
+    sample = np.stack([rng.randint(N, size=2 * B), rng.randint(R, size=2 * B), rng.randint(N, size=2 * B)], 1)
+    neg, w = rng.randint(N, size=(2 * B, K)), rng.uniform(0.1, 0.5, size=2 * B)
+    nc, rc = ko.entity_dim(model, D) // D, ko.relation_dim(model, D) // D
+    wd = D // world
+    c0 = rank * wd
+    cut = lambda t, comps: np.ascontiguousarray(t.reshape(t.shape[0], comps, D)[:, :, c0:c0 + wd].reshape(t.shape[0], comps * wd))
+    e_loc, r_loc = cut(ent, nc), cut(rel, rc)
+    part = np.concatenate([ko.score(model, e_loc, r_loc, sample, neg, "tail-batch", gamma=GAMMA),
+                           ko.score(model, e_loc, r_loc, sample, gamma=GAMMA)], axis=1)  # [2B, K + 1] partial scores
+    t = torch.from_numpy(part)
+    dist.all_reduce(t)  # the scheme's one exchange
+    full = t.numpy() - ((world - 1) * GAMMA if model == "TransE" else 0.0)
+    ngs, pos = full[:, :K], full[:, K]
+    gpos, gneg = ko.adversarial_loss_grads(pos, ngs, w)
+    ge1, gr1 = ko.score_grads(model, e_loc, r_loc, sample, None, None, gpos[:, None], gamma=GAMMA)[:2]
+    ge2, gr2 = ko.score_grads(model, e_loc, r_loc, sample, neg, "tail-batch", gneg, gamma=GAMMA)[:2]
+    parts_e = [torch.zeros(N, nc * wd, dtype=torch.float64) for _ in range(world)]
+    parts_r = [torch.zeros(R, rc * wd, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts_e, torch.from_numpy(ge1 + ge2))  # only to compare: the scheme itself never gathers
+    dist.all_gather(parts_r, torch.from_numpy(gr1 + gr2))
+    if rank == 0:
+        ge, gr = np.zeros_like(ent), np.zeros_like(rel)
+        for rr in range(world):
+            ge.reshape(N, nc, D)[:, :, rr * wd:(rr + 1) * wd] = parts_e[rr].numpy().reshape(N, nc, wd)
+            gr.reshape(R, rc, D)[:, :, rr * wd:(rr + 1) * wd] = parts_r[rr].numpy().reshape(R, rc, wd)
+        ref = ko.train_step(model, ent, rel, sample, neg, "tail-batch", w, gamma=GAMMA)
+        out["loss_err"] = abs(ko.adversarial_loss(pos, ngs, w) - ref[0])
+        out["ent_err"] = float(np.abs(ge - ref[3]).max() / np.abs(ref[3]).max())
+        out["rel_err"] = float(np.abs(gr - ref[4]).max() / np.abs(ref[4]).max())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("model", ("TransE", "ComplEx"))
+def test_two_rank_column_sharded_step_matches_single_process(model):
+    out = mp.Manager().dict()
+    mp.spawn(_colshard_worker, args=(2, _free_port(), out, model), nprocs=2, join=True)
+    assert out["loss_err"] < 1e-12 and out["ent_err"] < 1e-12 and out["rel_err"] < 1e-12, dict(out)
