@@ -284,7 +284,9 @@ int kge_pooled_dot_bwd(const kge_tables_t* tables, int mode, const int64_t* samp
  * filter may be NULL (raw ranking).  scores_out (optional, [Q, n_entity]) receives the biased
  * scores the reference would have sorted (filtered slots = s_pos - 1e5).
  * workspace: kge_rank_workspace_bytes(tables, Q) bytes of scratch (query vectors, positive scores,
- * filter segments); contents need not be initialised.
+ * filter segments and, for ComplEx / DistMult, a [Q, entity_dim] copy of the positives' rows: the
+ * tensor-core path scores them through the same GEMM as the candidates); contents need not be
+ * initialised.  Any number of entities (entity tiles fold over grid.y and grid.z).
  * ------------------------------------------------------------------------------------------- */
 size_t kge_rank_workspace_bytes(const kge_tables_t* tables, int64_t Q);
 int kge_rank_all(const kge_tables_t* tables, int mode, const int64_t* queries, int64_t Q,
